@@ -1,0 +1,353 @@
+/*
+ * expect_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY; see expect_oracle.h).
+ *
+ * Restates, in scalar C, the hot path of SciMLExpectations.jl:
+ *   prob_func  (reference src/expectation.jl:175-178, :277-280, :215-225, :304-314)
+ *   ODE/SDE solve (expectation.jl:191, :238, :290, :323 -> OrdinaryDiffEq / StochasticDiffEq,
+ *                  third-party, not vendored: semantics restated from the published
+ *                  algorithms -- Tsitouras 2011 5(4) pair, Hairer-Wanner initial step,
+ *                  PI step-size control, Euler-Maruyama)
+ *   output_func (expectation.jl:180, :227, :282, :316)
+ *   pdf        (src/distribution_utils.jl:42, :50 -> Distributions.logpdf)
+ *   reduction  (expectation.jl:194 per-node, :293 mean)
+ */
+#include "expect_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ---- Tsit5 tableau (Tsitouras 2011; the coefficients OrdinaryDiffEq's Tsit5 uses) ---- */
+static const double C1 = 0.161, C2 = 0.327, C3 = 0.9, C4 = 0.9800255409045097;
+static const double A21 = 0.161;
+static const double A31 = -0.008480655492356989, A32 = 0.335480655492357;
+static const double A41 = 2.8971530571054935, A42 = -6.359448489975075, A43 = 4.3622954328695815;
+static const double A51 = 5.325864828439257, A52 = -11.748883564062828, A53 = 7.4955393428898365,
+                    A54 = -0.09249506636175525;
+static const double A61 = 5.86145544294642, A62 = -12.92096931784711, A63 = 8.159367898576159,
+                    A64 = -0.071584973281401, A65 = -0.028269050394068383;
+static const double A71 = 0.09646076681806523, A72 = 0.01, A73 = 0.4798896504144996,
+                    A74 = 1.379008574103742, A75 = -3.290069515436081, A76 = 2.324710524099774;
+static const double BT1 = -0.00178001105222577714, BT2 = -0.0008164344596567469,
+                    BT3 = 0.007880878010261995, BT4 = -0.1447110071732629,
+                    BT5 = 0.5823571654525552, BT6 = -0.45808210592918697,
+                    BT7 = 0.015151515151515152;
+
+/* PI controller defaults for an order-5 explicit RK pair (OrdinaryDiffEq) */
+static const double BETA1 = 7.0 / 50.0, BETA2 = 2.0 / 25.0, GAMMA = 9.0 / 10.0;
+static const double QMIN = 1.0 / 5.0, QMAX = 10.0, QOLDINIT = 1e-4;
+
+static double ulp_of(double x) { x = fabs(x); return nextafter(x, INFINITY) - x; }
+
+/* RMS norm, OrdinaryDiffEq ODE_DEFAULT_NORM */
+static double rms(const double *v, int n) {
+    double s = 0;
+    for (int i = 0; i < n; i++) s += v[i] * v[i];
+    return sqrt(s / n);
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ---- Distributions.logpdf restated (distribution_utils.jl:42 sums these, then one exp) ---- */
+static double std_normal_cdf(double z) { return 0.5 * erfc(-z * M_SQRT1_2); }
+
+static double logpdf_1d(const orc_pdf_dim *d, double x) {
+    const double half_log_2pi = 0.91893853320467274178;
+    switch (d->kind) {
+    case ORC_PDF_NONE: return 0.0;
+    case ORC_PDF_UNIFORM:
+        return (x >= d->lo && x <= d->hi) ? -log(d->hi - d->lo) : -INFINITY;
+    case ORC_PDF_NORMAL: {
+        double z = (x - d->mu) / d->sigma;
+        return -0.5 * z * z - log(d->sigma) - half_log_2pi;
+    }
+    case ORC_PDF_TRUNCNORMAL: {
+        if (!(x >= d->lo && x <= d->hi)) return -INFINITY;
+        double z = (x - d->mu) / d->sigma;
+        double tp = std_normal_cdf((d->hi - d->mu) / d->sigma) -
+                    std_normal_cdf((d->lo - d->mu) / d->sigma);
+        return -0.5 * z * z - log(d->sigma) - half_log_2pi - log(tp);
+    }
+    }
+    return NAN;
+}
+
+double orc_logpdf(const orc_pdf_dim *pdf, int nx, const double *x) {
+    double s = 0;
+    for (int j = 0; j < nx; j++) s += logpdf_1d(&pdf[j], x[j]);
+    return s;
+}
+
+/* ---- KKL sine series, expectation.jl:217-220 / :306-309 (absolute t, no rescale) ---- */
+double orc_kkl_w(const double *z, int n, double t) {
+    double s = 0;
+    for (int k = 1; k <= n; k++) s += z[k - 1] * sin((k - 0.5) * M_PI * t) / ((k - 0.5) * M_PI);
+    return sqrt(2.0) * s;
+}
+
+/* ---- adaptive Tsit5, one trajectory.  Returns 0 ok / 1 failed; u updated in place ---- */
+static int tsit5_solve(const orc_problem *pb, double *u, const double *p, uint64_t *nf_out,
+                       uint64_t *nacc_out, uint64_t *nrej_out) {
+    const int n = pb->nstate;
+    const double t0 = pb->t0, t1 = pb->t1;
+    const double abstol = pb->abstol, reltol = pb->reltol;
+    const double dtmax = pb->dtmax > 0 ? pb->dtmax : (t1 - t0);
+    const int64_t maxiters = pb->maxiters > 0 ? pb->maxiters : 100000;
+    double k1[ORC_MAX_STATE], k2[ORC_MAX_STATE], k3[ORC_MAX_STATE], k4[ORC_MAX_STATE],
+        k5[ORC_MAX_STATE], k6[ORC_MAX_STATE], k7[ORC_MAX_STATE];
+    double tmp[ORC_MAX_STATE], unew[ORC_MAX_STATE], sk[ORC_MAX_STATE];
+    uint64_t nf = 0, nacc = 0, nrej = 0;
+    int failed = 0;
+    double t = t0;
+
+    /* Hairer-Wanner initial step as OrdinaryDiffEq's ode_determine_initdt does it */
+    double dt;
+    {
+        double *f0 = k1, *f1 = k2;
+        pb->rhs(f0, u, p, t);
+        nf++;
+        for (int i = 0; i < n; i++) sk[i] = abstol + fabs(u[i]) * reltol;
+        for (int i = 0; i < n; i++) tmp[i] = u[i] / sk[i];
+        double d0 = rms(tmp, n);
+        for (int i = 0; i < n; i++) tmp[i] = f0[i] / sk[i];
+        double d1 = rms(tmp, n);
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+        dt0 = fmin(dt0, dtmax);
+        if (dt0 < 10 * 2.220446049250313e-16) {
+            dt = 1e-6;
+        } else {
+            for (int i = 0; i < n; i++) unew[i] = u[i] + dt0 * f0[i];
+            pb->rhs(f1, unew, p, t + dt0);
+            nf++;
+            for (int i = 0; i < n; i++) tmp[i] = (f1[i] - f0[i]) / sk[i];
+            double d2 = rms(tmp, n) / dt0;
+            double dmax = fmax(d1, d2);
+            double dt1 = (dmax <= 1e-15) ? fmax(1e-6, dt0 * 1e-3)
+                                         : pow(10.0, -(2.0 + log10(dmax)) / 5.0);
+            dt = fmin(fmin(100.0 * dt0, dt1), dtmax);
+        }
+    }
+    /* Tsit5 initialize!: fsalfirst = f(uprev) */
+    pb->rhs(k1, u, p, t);
+    nf++;
+
+    double qold = QOLDINIT;
+    int64_t iter = 0;
+    while (t < t1) {
+        iter++;
+        if (iter > maxiters) { failed = 1; break; }
+        if (!(dt == dt) || !(fabs(dt) <= 1.79e308)) { failed = 1; break; } /* DtNaN */
+        dt = fmin(dt, dtmax);
+        dt = fmin(dt, t1 - t); /* modify_dt_for_tstops! */
+        if (t + dt == t) { failed = 1; break; } /* dt below resolution of t */
+
+        for (int i = 0; i < n; i++) tmp[i] = u[i] + dt * (A21 * k1[i]);
+        pb->rhs(k2, tmp, p, t + C1 * dt);
+        for (int i = 0; i < n; i++) tmp[i] = u[i] + dt * (A31 * k1[i] + A32 * k2[i]);
+        pb->rhs(k3, tmp, p, t + C2 * dt);
+        for (int i = 0; i < n; i++) tmp[i] = u[i] + dt * (A41 * k1[i] + A42 * k2[i] + A43 * k3[i]);
+        pb->rhs(k4, tmp, p, t + C3 * dt);
+        for (int i = 0; i < n; i++)
+            tmp[i] = u[i] + dt * (A51 * k1[i] + A52 * k2[i] + A53 * k3[i] + A54 * k4[i]);
+        pb->rhs(k5, tmp, p, t + C4 * dt);
+        for (int i = 0; i < n; i++)
+            tmp[i] = u[i] + dt * (A61 * k1[i] + A62 * k2[i] + A63 * k3[i] + A64 * k4[i] + A65 * k5[i]);
+        pb->rhs(k6, tmp, p, t + dt);
+        for (int i = 0; i < n; i++)
+            unew[i] = u[i] + dt * (A71 * k1[i] + A72 * k2[i] + A73 * k3[i] + A74 * k4[i] +
+                                   A75 * k5[i] + A76 * k6[i]);
+        pb->rhs(k7, unew, p, t + dt);
+        nf += 6;
+
+        /* embedded error, calculate_residuals + RMS norm */
+        double ss = 0;
+        for (int i = 0; i < n; i++) {
+            double ut = dt * (BT1 * k1[i] + BT2 * k2[i] + BT3 * k3[i] + BT4 * k4[i] + BT5 * k5[i] +
+                              BT6 * k6[i] + BT7 * k7[i]);
+            double r = ut / (abstol + fmax(fabs(u[i]), fabs(unew[i])) * reltol);
+            ss += r * r;
+        }
+        double EEst = sqrt(ss / n);
+
+        if (!(EEst == EEst)) { /* NaN error estimate: rejected, then dt becomes NaN -> abort */
+            nrej++;
+            failed = 1;
+            break;
+        }
+
+        /* PI controller (stepsize_controller!) */
+        double q, q11 = 0;
+        if (EEst == 0.0) {
+            q = 1.0 / QMAX;
+        } else {
+            q11 = pow(EEst, BETA1);
+            q = q11 / pow(qold, BETA2);
+            q = fmax(1.0 / QMAX, fmin(1.0 / QMIN, q / GAMMA));
+        }
+        if (EEst <= 1.0) {
+            /* step_accept_controller!: qsteady_min = qsteady_max = 1 */
+            if (q == 1.0) q = 1.0;
+            qold = fmax(EEst, QOLDINIT);
+            double dtnew = dt / q;
+            double ttmp = t + dt;
+            /* fixed_t_for_floatingpoint_error! */
+            if (fabs(ttmp - t1) < 100.0 * ulp_of(fmax(t, t1))) ttmp = t1;
+            t = ttmp;
+            for (int i = 0; i < n; i++) { u[i] = unew[i]; k1[i] = k7[i]; } /* FSAL */
+            dt = fmin(dtmax, dtnew); /* calc_dt_propose! */
+            nacc++;
+        } else {
+            /* step_reject_controller! */
+            dt = dt / fmin(1.0 / QMIN, q11 / GAMMA);
+            nrej++;
+        }
+    }
+    *nf_out += nf;
+    *nacc_out += nacc;
+    *nrej_out += nrej;
+    return failed;
+}
+
+/* ---- fixed-step Euler-Maruyama driven by the KKL path (scalar noise) ----
+ * u += f(u,p,t) dt + g(u,p,t) dW,  dW = W(t+dt) - W(t)  (DiffEqNoiseProcess NoiseFunction) */
+static int em_solve(const orc_problem *pb, double *u, const double *p, const double *z,
+                    uint64_t *nf_out, uint64_t *nacc_out) {
+    const int n = pb->nstate;
+    const double t0 = pb->t0, t1 = pb->t1, h = pb->dt_fixed;
+    int64_t nsteps = (int64_t)ceil((t1 - t0) / h - 1e-9);
+    double f[ORC_MAX_STATE], g[ORC_MAX_STATE];
+    double wcur = orc_kkl_w(z, pb->n_kkl, t0);
+    int failed = 0;
+    for (int64_t s = 0; s < nsteps; s++) {
+        double t = t0 + (double)s * h;
+        double tn = (s + 1 == nsteps) ? t1 : t0 + (double)(s + 1) * h;
+        double dt = tn - t;
+        double wn = orc_kkl_w(z, pb->n_kkl, tn);
+        double dW = wn - wcur;
+        wcur = wn;
+        pb->rhs(f, u, p, t);
+        pb->diffusion(g, u, p, t);
+        for (int i = 0; i < n; i++) u[i] = u[i] + dt * f[i] + g[i] * dW;
+    }
+    for (int i = 0; i < n; i++)
+        if (!(u[i] == u[i])) failed = 1;
+    *nf_out += (uint64_t)nsteps;
+    *nacc_out += (uint64_t)nsteps;
+    return failed;
+}
+
+static int solve_point_steps(const orc_problem *pb, const double *x, int weight_by_pdf, double *out,
+                             orc_counters *c, int32_t *steps) {
+    double u[ORC_MAX_STATE], p[ORC_MAX_PARAM], z[ORC_MAX_KKL];
+    uint64_t nf = 0, nacc = 0, nrej = 0;
+    int failed;
+    if (pb->solver == ORC_SOLVER_EM) {
+        /* expectation.jl:216: Z, p = h(x, u0, p); u0 stays nominal */
+        for (int i = 0; i < pb->nparam; i++) p[i] = pb->p_nom[i];
+        pb->hmap(x, pb->u0_nom, pb->p_nom, z, p);
+        for (int i = 0; i < pb->nstate; i++) u[i] = pb->u0_nom[i];
+        failed = em_solve(pb, u, p, z, &nf, &nacc);
+    } else {
+        /* expectation.jl:176: u0, p = h(x, prob.u0, prob.p) */
+        for (int i = 0; i < pb->nstate; i++) u[i] = pb->u0_nom[i];
+        for (int i = 0; i < pb->nparam; i++) p[i] = pb->p_nom[i];
+        pb->hmap(x, pb->u0_nom, pb->p_nom, u, p);
+        failed = tsit5_solve(pb, u, p, &nf, &nacc, &nrej);
+    }
+    pb->obs(u, p, pb->t1, out);
+    if (weight_by_pdf && pb->pdf) {
+        /* expectation.jl:180: g(sol, p) * pdf(d, x) */
+        double w = exp(orc_logpdf(pb->pdf, pb->nx, x));
+        for (int k = 0; k < pb->nout; k++) out[k] *= w;
+    }
+    if (c) { c->nf += nf; c->naccept += nacc; c->nreject += nrej; c->nfail += (uint64_t)failed; }
+    if (steps) *steps = (int32_t)(nacc + nrej);
+    return failed;
+}
+
+int orc_solve_point(const orc_problem *pb, const double *x, int weight_by_pdf, double *out,
+                    orc_counters *c) {
+    return solve_point_steps(pb, x, weight_by_pdf, out, c, NULL);
+}
+
+static void gather_x(const double *x, int64_t npts, int nx, int layout, int64_t i, double *xi) {
+    if (layout == 0) for (int j = 0; j < nx; j++) xi[j] = x[i * nx + j];
+    else for (int j = 0; j < nx; j++) xi[j] = x[(int64_t)j * npts + i];
+}
+
+int orc_eval_nodes(const orc_problem *pb, const double *x, int64_t npts, int layout,
+                   int weight_by_pdf, double *dx, orc_counters *c, int32_t *per_point_steps,
+                   int nthreads) {
+    uint64_t nf = 0, nacc = 0, nrej = 0, nfail = 0;
+    const int nx = pb->nx, nout = pb->nout;
+    if (nthreads <= 0) nthreads = orc_max_threads();
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads) \
+    reduction(+ : nf, nacc, nrej, nfail)
+    for (int64_t i = 0; i < npts; i++) {
+        double xi[ORC_MAX_X], out[ORC_MAX_OUT];
+        orc_counters ci = {0, 0, 0, 0};
+        gather_x(x, npts, nx, layout, i, xi);
+        solve_point_steps(pb, xi, weight_by_pdf, out, &ci, per_point_steps ? &per_point_steps[i] : NULL);
+        if (layout == 0) for (int k = 0; k < nout; k++) dx[i * nout + k] = out[k];
+        else for (int k = 0; k < nout; k++) dx[(int64_t)k * npts + i] = out[k];
+        nf += ci.nf; nacc += ci.naccept; nrej += ci.nreject; nfail += ci.nfail;
+    }
+    if (c) { c->nf += nf; c->naccept += nacc; c->nreject += nrej; c->nfail += nfail; }
+    return 0;
+}
+
+/* Neumaier compensated add */
+static inline void nadd(double *s, double *comp, double v) {
+    double t = *s + v;
+    if (fabs(*s) >= fabs(v)) *comp += (*s - t) + v;
+    else *comp += (v - t) + *s;
+    *s = t;
+}
+
+int orc_reduce_samples(const orc_problem *pb, const double *x, int64_t n, int layout,
+                       int weight_by_pdf, double *sum, double *sumsq, orc_counters *c,
+                       int nthreads) {
+    const int nx = pb->nx, nout = pb->nout;
+    const int64_t CH = 4096;
+    const int64_t nchunks = (n + CH - 1) / CH;
+    uint64_t nf = 0, nacc = 0, nrej = 0, nfail = 0;
+    double *cs = (double *)calloc((size_t)nchunks * 2 * nout + 1, sizeof(double));
+    if (!cs) return -1;
+    if (nthreads <= 0) nthreads = orc_max_threads();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads) \
+    reduction(+ : nf, nacc, nrej, nfail)
+    for (int64_t ch = 0; ch < nchunks; ch++) {
+        double s[2 * ORC_MAX_OUT] = {0}, comp[2 * ORC_MAX_OUT] = {0};
+        int64_t lo = ch * CH, hi = lo + CH < n ? lo + CH : n;
+        for (int64_t i = lo; i < hi; i++) {
+            double xi[ORC_MAX_X], out[ORC_MAX_OUT];
+            orc_counters ci = {0, 0, 0, 0};
+            gather_x(x, n, nx, layout, i, xi);
+            solve_point_steps(pb, xi, weight_by_pdf, out, &ci, NULL);
+            for (int k = 0; k < nout; k++) {
+                nadd(&s[k], &comp[k], out[k]);
+                nadd(&s[nout + k], &comp[nout + k], out[k] * out[k]);
+            }
+            nf += ci.nf; nacc += ci.naccept; nrej += ci.nreject; nfail += ci.nfail;
+        }
+        for (int k = 0; k < 2 * nout; k++) cs[ch * 2 * nout + k] = s[k] + comp[k];
+    }
+    for (int k = 0; k < 2 * nout; k++) {
+        double s = 0, comp = 0;
+        for (int64_t ch = 0; ch < nchunks; ch++) nadd(&s, &comp, cs[ch * 2 * nout + k]);
+        if (k < nout) sum[k] = s + comp;
+        else if (sumsq) sumsq[k - nout] = s + comp;
+    }
+    free(cs);
+    if (c) { c->nf += nf; c->naccept += nacc; c->nreject += nrej; c->nfail += nfail; }
+    return 0;
+}
