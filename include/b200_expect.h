@@ -1,0 +1,182 @@
+/*
+ * b200_expect.h -- C ABI of libb200expect.so: the B200-native drop-in for the batched
+ * expectation integrand of SciMLExpectations.jl.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference repo):
+ *
+ *   b200e_create          <- SystemMap(prob, alg, ensemblealg; kwargs...)     src/system_utils.jl:32-53
+ *                            + ExpectationProblem(sm, g, h, d)                src/problem_types.jl:60-66, :81-85
+ *                            + GenericDistribution(dists...)                  src/distribution_utils.jl:40-48
+ *                            (the data the hot path closes over: template problem, solver and its
+ *                             kwargs, covariate map h, observable g, product density d)
+ *   b200e_eval_nodes      <- integrand_koopman_systemmap_batch!(dx, x, p)     src/expectation.jl:182-196
+ *                            and its process-noise twin                       src/expectation.jl:229-243
+ *                            (the f!(dx, x, p) Integrals.jl calls once per cubature refinement round)
+ *   b200e_reduce_samples  <- solve(exprob, MonteCarlo(n)): the EnsembleProblem solve + mean(sol.u)
+ *                                                                             src/expectation.jl:277-293, :304-324
+ *   b200e_reduce_regions  <- the Genz-Malik rule Cubature applies to dx (callers either side of the
+ *                            path)
+ *
+ * Conventions: every function returns 0 on success and a negative B200E_ERR_* code on failure;
+ * b200e_last_error(h) returns a message owned by the library.  All host buffers are caller-owned;
+ * the library copies in/out inside the call and keeps no caller pointer after it returns.  Calls on
+ * one handle are serialised by the caller; distinct handles may be used from distinct threads.
+ * x / dx / sum pointers may be HOST pointers (pageable or pinned) or DEVICE pointers on the
+ * handle's device (detected with cudaPointerGetAttributes); device pointers skip the copies.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef B200_EXPECT_H
+#define B200_EXPECT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200E_ABI_VERSION 1
+
+/* limits (compile-time dims of the generated kernel) */
+#define B200E_MAX_STATE 16
+#define B200E_MAX_PARAM 32
+#define B200E_MAX_X 32
+#define B200E_MAX_OUT 16
+#define B200E_MAX_KKL 32
+
+enum {
+    B200E_OK = 0,
+    B200E_ERR_INVALID = -1,   /* bad argument / dimension */
+    B200E_ERR_COMPILE = -2,   /* NVRTC failed; see b200e_compile_log */
+    B200E_ERR_CUDA = -3,      /* CUDA runtime/driver error */
+    B200E_ERR_NO_DEVICE = -4, /* no usable CUDA device (there is no CPU fallback) */
+    B200E_ERR_NOMEM = -5,
+    B200E_ERR_NCCL = -6
+};
+
+enum { B200E_SOLVER_TSIT5 = 0, B200E_SOLVER_EM = 1 };
+enum { B200E_FP64 = 0, B200E_FP32 = 1 };
+/* layout of x (and dx): 0 = point-major x[i*nx+j] (what Julia's dim x npts column-major array is),
+ *                        1 = SoA x[j*npts+i] */
+enum { B200E_LAYOUT_POINT_MAJOR = 0, B200E_LAYOUT_SOA = 1 };
+enum { B200E_PDF_NONE = 0, B200E_PDF_UNIFORM = 1, B200E_PDF_NORMAL = 2, B200E_PDF_TRUNCNORMAL = 3 };
+
+/* one factor of GenericDistribution(dists...) (src/distribution_utils.jl:40-48) */
+typedef struct {
+    int32_t kind; /* B200E_PDF_* */
+    int32_t _pad;
+    double lo, hi;    /* support: uniform bounds / truncation bounds (+-inf for plain normal) */
+    double mu, sigma; /* normal parameters */
+} b200e_pdf_dim;
+
+/*
+ * Everything the hot path closes over.  `source` holds CUDA device functions, compiled by NVRTC
+ * for sm_100a into the generated kernel (arbitrary Julia closures cannot cross a C ABI):
+ *
+ *   B200E_FN void rhs(real* du, const real* u, const real* p, real t);                (ODE f / SDE drift)
+ *   B200E_FN void hmap(const real* x, const real* u0_nom, const real* p_nom,
+ *                      real* u0_or_Z, real* p);                 (h, expectation.jl:176, :216)
+ *   B200E_FN void observable(const real* u_end, const real* p, real t_end, real* out); (g, end-state form)
+ *   B200E_FN void diffusion(real* g, const real* u, const real* p, real t);           (EM only; scalar noise)
+ *
+ * u0/p outputs of hmap are pre-filled with the nominal values, so hmap only writes what it changes.
+ */
+typedef struct {
+    uint32_t struct_size; /* sizeof(b200e_model), for ABI evolution */
+    int32_t nstate, nparam, nx, nout;
+    int32_t solver;  /* B200E_SOLVER_* */
+    int32_t n_kkl;   /* EM: number of KKL terms (length of Z); 0 for Tsit5 */
+    int32_t fp_mode; /* B200E_FP64 / B200E_FP32 (state arithmetic; accumulation is always f64) */
+    const char *source;
+    const double *u0; /* nominal initial condition, nstate entries (prob.u0) */
+    const double *p;  /* nominal parameters, nparam entries (prob.p) */
+    double t0, t1;    /* prob.tspan */
+    double abstol, reltol; /* Tsit5 tolerances (OrdinaryDiffEq defaults 1e-6 / 1e-3) */
+    double dtmax;          /* <= 0 -> t1 - t0 */
+    double dt_fixed;       /* EM step */
+    int64_t maxiters;      /* <= 0 -> 100000 */
+    const b200e_pdf_dim *pdf; /* nx entries, or NULL for weight 1 */
+    /* placement and launch shape (0 = library default) */
+    int32_t n_devices;        /* 0/1: single device */
+    const int32_t *devices;   /* CUDA ordinals; NULL -> current device (n_devices<=1) or 0..n-1 */
+    int32_t block_size;       /* threads per block, multiple of 32 */
+    int32_t blocks_per_sm;    /* resident blocks per SM to launch (grid = SMs * this) */
+    int32_t refill_threshold; /* lanes of a warp that must be idle before the warp reloads (1..32) */
+    int32_t chunk_points;     /* host-pointer calls are pipelined in chunks of this many points */
+    const char *cache_dir;    /* cubin cache directory, NULL -> $B200E_CACHE_DIR or disabled */
+} b200e_model;
+
+typedef struct {
+    uint64_t nf;      /* RHS evaluations */
+    uint64_t naccept; /* accepted steps */
+    uint64_t nreject; /* rejected steps */
+    uint64_t nfail;   /* trajectories aborted (maxiters / non-finite / dt underflow) */
+} b200e_counters;
+
+/* timing/shape of the most recent call on a handle (filled from CUDA events on the launch stream) */
+typedef struct {
+    double kernel_ms;   /* sum of main-kernel durations of the last call (device 0 of the handle) */
+    double total_ms;    /* first enqueue -> last completion, CUDA events */
+    int64_t launches;   /* kernel launches (main + finalize) in the last call */
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t grid, block, regs_per_thread, blocks_per_sm_occ;
+    int32_t local_bytes_per_thread, smem_bytes;
+} b200e_call_stats;
+
+typedef struct b200e_handle b200e_handle;
+
+int b200e_abi_version(void);
+
+/* NVRTC-compile the model for sm_100a (cached by content hash) and set up device state. */
+int b200e_create(const b200e_model *model, b200e_handle **out);
+int b200e_destroy(b200e_handle *h);
+
+/* Compile only (needs no GPU): returns the cubin size and leaves the ptxas/NVRTC log in
+ * b200e_last_error(NULL).  Used by build() to cross-check models for sm_100a on a CPU box. */
+int b200e_compile_check(const b200e_model *model, int64_t *cubin_bytes);
+
+/* message of the last failure on this handle (h == NULL: last failure of create/compile_check
+ * on the calling thread).  Never NULL. */
+const char *b200e_last_error(const b200e_handle *h);
+/* NVRTC + ptxas -v log of the handle's kernel */
+const char *b200e_compile_log(const b200e_handle *h);
+
+/* Koopman batch integrand: dx[:, i] = g(sol_i, p_i) * pdf(d, x[:, i])  (weight_by_pdf != 0)
+ * Blocking: dx is completely written when the call returns. */
+int b200e_eval_nodes(b200e_handle *h, const double *x, int64_t npts, int32_t layout,
+                     int32_t weight_by_pdf, double *dx);
+
+/* MonteCarlo block: sum[k] = sum_i g_k(sol_i, p_i) [* pdf], sumsq[k] = sum_i (.)^2 (may be NULL),
+ * counters may be NULL.  The caller divides by n (mean(sol.u), expectation.jl:293).
+ * With n_devices > 1 the samples are sharded in contiguous index ranges and the per-device
+ * partial sums are combined by one NCCL all-reduce. */
+int b200e_reduce_samples(b200e_handle *h, const double *x, int64_t n, int32_t layout,
+                         int32_t weight_by_pdf, double *sum, double *sumsq, b200e_counters *c);
+
+/* counters of the last b200e_eval_nodes call */
+int b200e_last_counters(const b200e_handle *h, b200e_counters *c);
+int b200e_last_stats(const b200e_handle *h, b200e_call_stats *s);
+
+/* optional per-point diagnostics of the next eval_nodes call: attempted steps per point
+ * (host int32 buffer of npts entries; NULL disables) */
+int b200e_set_steps_buffer(b200e_handle *h, int32_t *steps);
+
+/* pinned host memory for callers that want true async H2D (cudaHostAlloc / cudaFreeHost) */
+int b200e_host_alloc(void **ptr, int64_t bytes);
+int b200e_host_free(void *ptr);
+/* device memory on the handle's (first) device, for keeping sample sets resident in HBM */
+int b200e_device_alloc(b200e_handle *h, void **dptr, int64_t bytes);
+int b200e_device_free(b200e_handle *h, void *dptr);
+int b200e_memcpy_h2d(b200e_handle *h, void *dptr, const void *src, int64_t bytes);
+int b200e_memcpy_d2h(b200e_handle *h, void *dst, const void *dptr, int64_t bytes);
+
+/* FP64 (fp32 != 0: FP32) FMA-chain microbenchmark on the handle's device: the measured
+ * roofline denominator for this path (MEASURED_PEAKS.json has no FP64 entry). */
+int b200e_measure_fma_peak(int32_t device, int32_t fp32, double *tflops);
+
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int b200e_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

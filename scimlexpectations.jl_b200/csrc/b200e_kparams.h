@@ -1,0 +1,43 @@
+// b200e_kparams.h -- launch parameters shared verbatim by the host library (nvcc) and the
+// NVRTC-generated kernels.  Plain C types only (NVRTC has no <stdint.h>); every field is naturally
+// aligned so host and device layouts agree.
+#ifndef B200E_KPARAMS_H
+#define B200E_KPARAMS_H
+
+#define B200E_KP_MAX_STATE 16
+#define B200E_KP_MAX_PARAM 32
+#define B200E_KP_MAX_X 32
+
+// device form of one factor of the product density: logpdf(x) = logc - 0.5*((x-mu)*inv_sigma)^2
+// inside [lo,hi], -inf outside.  logc folds -log(sigma) - log(2pi)/2 - log(cdf(hi)-cdf(lo))
+// (or -log(hi-lo) for uniform, where inv_sigma = 0) and is computed once on the host.
+struct b200e_kpdf {
+    double lo, hi, mu, inv_sigma, logc;
+    int kind;
+    int _pad;
+};
+
+struct b200e_kparams {
+    const double *x;        // sample points / cubature nodes (device)
+    double *dx;             // per-node outputs (nodes mode)
+    double *partials;       // [grid][2*nout] per-block partial sums (reduce mode)
+    unsigned long long *cpartials;  // [grid][4] per-block counters
+    int *steps;             // optional per-point attempted steps (nodes mode), or null
+    const double *kkl_table;  // EM: [nsteps+1][n_kkl] basis values sqrt(2) sin((k-1/2) pi t_n)/((k-1/2) pi)
+    long long npts;         // points in this launch
+    long long ld;           // SoA leading dimension of x and dx (total points of the caller's array)
+    long long maxiters;
+    long long em_nsteps;
+    double t0, t1;
+    double abstol, reltol, dtmax, dt_fixed;
+    double snap_tol;        // 100 * ulp(|t1|): end-point snapping of the last step
+    int layout;             // 0 point-major, 1 SoA
+    int weight_by_pdf;
+    int refill_threshold;
+    int want_sumsq;
+    double u0_nom[B200E_KP_MAX_STATE];
+    double p_nom[B200E_KP_MAX_PARAM];
+    b200e_kpdf pdf[B200E_KP_MAX_X];
+};
+
+#endif
