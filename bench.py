@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- ODE-solve integrand evals/s of the batched expectation integrand on B200.
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+    b200e_reduce_samples over the rank's sample set (h -> Tsit5 solve -> g -> sum) followed, for
+    N > 1, by the all-reduce of the 2*nout partial sums + 4 counters (NCCL via torch.distributed).
+Default workload = BASELINE.json configs[1]: the README 2-state linear ODE, MonteCarlo(10^7) on a
+shared host-generated sample set (seeded, block-keyed; tests/sampling_util.py).  Each rank owns its
+own 10^7-sample blocks of the stream ("scaling": "weak", no data-path collective besides the final
+all-reduce of O(10) numbers).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+--impl reference times the CPU restatement of the reference path (oracle/, OpenMP over all host
+cores -- the decomposition EnsembleThreads uses) on a bounded sample of the same workload: Julia is
+not in this image, so the reference itself cannot run.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests.sampling_util import BLOCK, sample_block  # noqa: E402
+
+WORKLOADS = {
+    # name: (model, samples per rank per step, description)
+    "linear2_mc1e7": ("linear2", 10_000_000, "README 2-state linear ODE du=A*u, MonteCarlo(10^7), Tsit5 abstol=1e-6 reltol=1e-3"),
+    "lorenz63_mc": ("lorenz63", 16_000_000, "Lorenz-63, 3 uncertain params + 3 uncertain u0, MonteCarlo block of 1.6e7 (C4 streams 10^9 in such blocks)"),
+    "lotka_volterra_mc": ("lotka_volterra", 8_000_000, "Lotka-Volterra 4 uncertain params, MonteCarlo(8e6)"),
+    "oscillator_noise_mc": ("oscillator_noise", 2_000_000, "KKL process-noise damped oscillator, Euler-Maruyama dt=2^-10, MonteCarlo(2e6)"),
+}
+F_RHS = {"linear2": 6, "lotka_volterra": 6, "lorenz63": 8, "decay1": 1, "oscillator_noise": 7, "gbm4": 0}
+
+
+def algorithmic_flops(model: str, spec, counters: dict, npts: int) -> float:
+    """F = nf*F_rhs + n_attempt*(70n+12) + npts*(12n+10) + npts*F_obs (FMA = 2)."""
+    n = spec.nstate
+    if spec.solver == 0:
+        att = counters["naccept"] + counters["nreject"]
+        return counters["nf"] * F_RHS[model] + att * (70 * n + 12) + npts * (12 * n + 10) + npts * spec.nout
+    # Euler-Maruyama: per step 2*n_kkl (dW from the table) + F_f + F_g + 4n
+    return counters["naccept"] * (2 * spec.n_kkl + F_RHS[model] + 4 * n) + npts * spec.nout
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def make_samples(model: str, n: int, seed: int, first_block: int, out: np.ndarray):
+    """Fill out[(n, nx)] with blocks first_block.. of the seeded stream."""
+    got, b = 0, first_block
+    while got < n:
+        m = min(BLOCK, n - got)
+        out[got:got + m] = sample_block(model, seed, b)[:m]
+        got += m
+        b += 1
+
+
+def cpu_restatement_rate(model: str, n_sample: int, seed: int = 7):
+    """Times the oracle (CPU restatement of the reference path) on all host cores.  Returns
+    (evals/s, cores, n, seconds)."""
+    import oracle
+    orc = oracle.OracleProblem.builtin(model)
+    cores = oracle.max_threads()
+    x = np.empty((n_sample, orc.nx))
+    make_samples(model, n_sample, seed, 0, x)
+    orc.reduce_samples(x[: min(n_sample, 1 << 16)])  # warm-up (page in, spin threads)
+    t0 = time.perf_counter()
+    orc.reduce_samples(x)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, cores, n_sample, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    model, n_full, desc = WORKLOADS[args.workload]
+    import oracle
+    orc = oracle.OracleProblem.builtin(model)
+    cores = oracle.max_threads()
+    # bounded sample per step: ~2 s of CPU work, calibrated on a small block
+    x_cal = np.empty((1 << 17, orc.nx))
+    make_samples(model, len(x_cal), 7, 0, x_cal)
+    orc.reduce_samples(x_cal)
+    t0 = time.perf_counter()
+    orc.reduce_samples(x_cal)
+    rate = len(x_cal) / (time.perf_counter() - t0)
+    n = int(min(n_full, max(1 << 17, rate * 2.0)))
+    x = np.empty((n, orc.nx))
+    make_samples(model, n, 7, 0, x)
+    for _ in range(args.warmup):
+        orc.reduce_samples(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s, s2, c = orc.reduce_samples(x)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "ODE-solve integrand evals/sec", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "model": model, "description": desc,
+                   "samples_per_step": n, "note": "bounded sample of the workload; CPU restatement of the reference's "
+                   "EnsembleThreads path (Julia is not installed in this image, the reference cannot run)"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} samples of {args.workload} per step, OpenMP over {cores} threads"},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import scimlexpectations_jl_b200 as sme
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; this path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    model, n, desc = WORKLOADS[args.workload]
+    if args.samples:
+        n = args.samples
+    spec = sme.models.builtin(model, devices=[local_rank], refill_threshold=args.refill,
+                              block_size=args.block, blocks_per_sm=args.blocks_per_sm,
+                              fp_mode=1 if args.fp32 else 0)
+    h = sme.Handle(spec)
+    nx, nout = spec.nx, spec.nout
+
+    # rank r owns blocks [r*nb, (r+1)*nb) of the seeded stream: same sets the CPU oracle sees in tests
+    nb = (n + BLOCK - 1) // BLOCK
+    xp = h.pinned((n, nx))
+    make_samples(model, n, args.seed, rank * nb, xp.array)
+    xd = h.device_array((n, nx)).upload(xp.array)
+
+    red = torch.zeros(2 * nout + 4, dtype=torch.float64, device="cuda")
+
+    def step_resident():
+        s, s2, c = h.reduce_samples(xd, npts=n)
+        st = h.last_stats()
+        if world > 1:
+            red[:nout] = torch.from_numpy(s)
+            red[nout:2 * nout] = torch.from_numpy(s2)
+            red[2 * nout:] = torch.tensor([c["nf"], c["naccept"], c["nreject"], c["nfail"]], dtype=torch.float64)
+            dist.all_reduce(red)
+        return s, s2, c, st
+
+    def step_e2e():
+        s, s2, c = h.reduce_samples(xp)  # pinned host buffer: H2D inside the call, sums come back D2H
+        st = h.last_stats()
+        if world > 1:
+            red[:nout] = torch.from_numpy(s)
+            red[nout:2 * nout] = torch.from_numpy(s2)
+            red[2 * nout:] = torch.tensor([c["nf"], c["naccept"], c["nreject"], c["nfail"]], dtype=torch.float64)
+            dist.all_reduce(red)
+            torch.cuda.synchronize()
+        return s, s2, c, st
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        kernel_ms, total_ms, launches = [], [], 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            s, s2, c, st = fn()
+            kernel_ms.append(st["kernel_ms"])
+            total_ms.append(st["total_ms"])
+            launches += st["launches"]
+        torch.cuda.synchronize()
+        t_local = time.perf_counter() - t0
+        barrier()
+        t = torch.tensor([t_local], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), kernel_ms, total_ms, launches, (s, s2, c, st)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    T, kernel_ms, total_ms, launches, (s, s2, c, st) = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop()
+    Te, _, e_total_ms, _, (se, s2e, ce, ste) = timed(step_e2e, max(3, args.steps // 4), 3)
+    e_steps = max(3, args.steps // 4)
+
+    value = world * n * args.steps / T
+    e2e_value = world * n * e_steps / Te
+    k_ms = float(np.mean(kernel_ms))
+    flops = algorithmic_flops(model, spec, c, n)
+    peak = sme.measure_fma_peak(local_rank, args.fp32)
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak = json.load(open(peaks_path)).get("hbm_gbs") if os.path.exists(peaks_path) else 6650.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+
+    if rank == 0:
+        mean = s / n
+        line = {
+            "metric": "ODE-solve integrand evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": T / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "model": model, "description": desc,
+                       "samples_per_gpu_per_step": n, "sample_set": f"PCG64(SeedSequence([{args.seed}, block])), blocks of 2^20",
+                       "l2": f"input {n * nx * 8 / 1e6:.0f} MB per GPU > 126 MB L2" if n * nx * 8 > 126e6 else "input smaller than L2",
+                       "grid": st["grid"], "block": st["block"], "regs": st["regs_per_thread"],
+                       "refill_threshold": args.refill or 32, "parallelism": f"samples sharded over {world} GPU(s)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(ste["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(ste["d2h_bytes"]), "ms_per_step": Te / e_steps * 1e3,
+                    "api": "b200e_reduce_samples(host pinned x) -> host sums"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64" if not args.fp32 else "fp32", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "kernel": "b200e_reduce", "kernel_ms": k_ms,
+                         "flops_per_launch": flops,
+                         "peak_source": "b200e_measure_fma_peak (FMA-chain microbenchmark run in this process; "
+                                        "MEASURED_PEAKS.json has no FP64 entry)",
+                         "hbm": {"achieved": n * nx * 8 / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}},
+            "counters": c, "expectation": mean.tolist(),
+            "device_ms_per_step": float(np.mean(total_ms)),
+        }
+        if world == 1 and not args.no_cpu:
+            # ~10-20 s of CPU work on the box's host cores
+            r0, cores, _, _ = cpu_restatement_rate(model, 1 << 18)
+            ncpu = int(min(n, max(1 << 18, r0 * 12.0)))
+            rate, cores, ncpu, secs = cpu_restatement_rate(model, ncpu)
+            line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                                    "sample": f"first {ncpu} samples of the same sample set, {secs:.1f} s, "
+                                              "oracle/ (C restatement, OpenMP)"}
+        print(json.dumps(line))
+    xd.free()
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="linear2_mc1e7", choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0, help="override samples per GPU per step")
+    ap.add_argument("--seed", type=int, default=20261019)
+    ap.add_argument("--refill", type=int, default=0)
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--blocks-per-sm", type=int, default=0)
+    ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

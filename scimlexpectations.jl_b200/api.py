@@ -1,0 +1,410 @@
+"""Host-side mirror of the reference's public interface for the batched-integrand path.
+
+Same names, argument order and semantics as SciMLExpectations.jl (the Julia toolchain is absent from
+this image, so the host side above the C ABI is Python here and a ``ccall`` shim in
+``julia/B200Expectations.jl``):
+
+    GenericDistribution(dists...)                      src/distribution_utils.jl:33-54
+    SystemMap(prob, alg, ensemblealg; kwargs...)       src/system_utils.jl:32-62
+    ProcessNoiseSystemMap(prob, n, args...; kwargs...) src/system_utils.jl:92-117
+    ExpectationProblem(sm, g, h, d)                    src/problem_types.jl:41-85
+    solve(exprob, Koopman(); batch, quadalg, ireltol, iabstol, maxiters)   src/expectation.jl:336-354
+    solve(exprob, MonteCarlo(n))                       src/expectation.jl:268-325
+    build_integrand(exprob, Koopman(), mid, p, batch)  src/expectation.jl:169-200, :209-249
+    ExpectationSolution(u, resid, original)            src/solution_types.jl:14-18
+
+What changes relative to the reference is only what sits in the ``ensemblealg`` slot:
+``EnsembleB200()``.  Arbitrary host closures cannot run on the device, so ``f`` (the ODE right-hand
+side), ``g`` (observable) and ``h`` (covariate map) are given as CUDA device-function source in the
+dialect of ``csrc/kernels/expect_prelude.cuh`` -- or built from the structured helpers
+``models.hmap_scatter`` / ``models.observable_components``.  There is no CPU fallback: without the
+CUDA library and a B200 ``solve`` raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Callable, Optional, Sequence
+
+import numpy as np
+from scipy.special import ndtr, ndtri
+
+from . import _capi
+from ._capi import FP32, FP64, LAYOUT_POINT_MAJOR, ModelSpec, PDF_NONE, PDF_NORMAL, PDF_TRUNCNORMAL, PDF_UNIFORM
+from .cubature import CubatureResult, hcubature_v
+
+# ---------------------------------------------------------------------------------------------
+# distributions (the subset of Distributions.jl the product density table covers)
+# ---------------------------------------------------------------------------------------------
+
+
+@dataclass(frozen=True)
+class Uniform:
+    a: float = 0.0
+    b: float = 1.0
+
+    def minimum(self): return float(self.a)
+    def maximum(self): return float(self.b)
+    def logpdf(self, x): return -math.log(self.b - self.a) if self.a <= x <= self.b else -math.inf
+    def icdf(self, u): return self.a + (self.b - self.a) * u
+    def table(self): return (PDF_UNIFORM, self.a, self.b, 0.0, 1.0)
+
+
+@dataclass(frozen=True)
+class Normal:
+    mu: float = 0.0
+    sigma: float = 1.0
+
+    def minimum(self): return -math.inf
+    def maximum(self): return math.inf
+
+    def logpdf(self, x):
+        z = (x - self.mu) / self.sigma
+        return -0.5 * z * z - math.log(self.sigma) - 0.5 * math.log(2.0 * math.pi)
+
+    def icdf(self, u): return self.mu + self.sigma * ndtri(u)
+    def table(self): return (PDF_NORMAL, -math.inf, math.inf, self.mu, self.sigma)
+
+
+@dataclass(frozen=True)
+class Truncated:
+    """``truncated(Normal(mu, sigma), lower, upper)``"""
+    untruncated: Normal
+    lower: float
+    upper: float
+
+    def minimum(self): return float(self.lower)
+    def maximum(self): return float(self.upper)
+
+    def _tp(self):
+        d = self.untruncated
+        return float(ndtr((self.upper - d.mu) / d.sigma) - ndtr((self.lower - d.mu) / d.sigma))
+
+    def logpdf(self, x):
+        if not (self.lower <= x <= self.upper):
+            return -math.inf
+        return self.untruncated.logpdf(x) - math.log(self._tp())
+
+    def icdf(self, u):
+        d = self.untruncated
+        a, b = ndtr((self.lower - d.mu) / d.sigma), ndtr((self.upper - d.mu) / d.sigma)
+        return np.clip(d.mu + d.sigma * ndtri(a + (b - a) * u), self.lower, self.upper)
+
+    def table(self):
+        return (PDF_TRUNCNORMAL, self.lower, self.upper, self.untruncated.mu, self.untruncated.sigma)
+
+
+def truncated(d: Normal, lower: float, upper: float) -> Truncated:
+    if not isinstance(d, Normal):
+        raise TypeError("only truncated Normal distributions are tabulated for the device pdf")
+    return Truncated(d, float(lower), float(upper))
+
+
+class GenericDistribution:
+    """Product of independent univariate distributions (reference distribution_utils.jl:40-48):
+    ``pdf_func(x) = exp(sum(logpdf(f, y)))``, ``rand_func() = [rand(d) for d in dists]``,
+    ``lb/ub = minimum/maximum`` of the factors."""
+
+    def __init__(self, d, *ds):
+        self.dists = (d,) + tuple(ds)
+        self.lb = np.array([x.minimum() for x in self.dists], dtype=np.float64)
+        self.ub = np.array([x.maximum() for x in self.dists], dtype=np.float64)
+        self._rng = np.random.default_rng()
+
+    def pdf_func(self, x):
+        return math.exp(sum(f.logpdf(float(y)) for f, y in zip(self.dists, x)))
+
+    def rand_func(self):
+        return np.array([d.icdf(self._rng.random()) for d in self.dists])
+
+    def table(self):
+        return [d.table() for d in self.dists]
+
+    def __len__(self):
+        return len(self.dists)
+
+    # host-generated sample sets: block b of the stream is a pure function of (seed, b)
+    def rand_block(self, seed: int, block: int, n: int) -> np.ndarray:
+        rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence([int(seed), int(block)])))
+        u = rng.random((n, len(self.dists)))
+        out = np.empty_like(u)
+        for j, d in enumerate(self.dists):
+            out[:, j] = d.icdf(u[:, j])
+        return out
+
+
+def pdf(d: GenericDistribution, x): return d.pdf_func(x)
+def minimum(d: GenericDistribution): return d.lb
+def maximum(d: GenericDistribution): return d.ub
+def extrema(d: GenericDistribution): return d.lb, d.ub
+def rand(d: GenericDistribution): return d.rand_func()
+
+
+# ---------------------------------------------------------------------------------------------
+# problems, solvers, ensemble algorithm
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class ODEProblem:
+    """``ODEProblem(f, u0, tspan, p)``; ``f`` is CUDA source defining ``rhs(du,u,p,t)``."""
+    f: str
+    u0: Sequence[float]
+    tspan: Sequence[float]
+    p: Sequence[float] = ()
+
+
+@dataclass
+class SDEProblem:
+    """``SDEProblem(f, g, u0, tspan, p)`` with scalar noise; ``f``/``g`` are CUDA sources defining
+    ``rhs`` and ``diffusion`` (the scalar dW multiplies every component, test/processnoise.jl:9-14)."""
+    f: str
+    g: str
+    u0: Sequence[float]
+    tspan: Sequence[float]
+    p: Sequence[float] = ()
+
+
+@dataclass(frozen=True)
+class Tsit5:
+    pass
+
+
+@dataclass(frozen=True)
+class EM:
+    """Fixed-step Euler-Maruyama; ``dt`` may also be passed as the solve kwarg ``dt=``."""
+    dt: float = 0.0
+
+
+@dataclass
+class EnsembleB200:
+    """The ``ensemblealg`` that routes the ensemble solve to libb200expect (``<: EnsembleAlgorithm``
+    in the Julia shim).  Launch-shape fields are 0 for the library defaults."""
+    devices: Optional[Sequence[int]] = None
+    fp32: bool = False
+    block_size: int = 0
+    blocks_per_sm: int = 0
+    refill_threshold: int = 0
+    chunk_points: int = 0
+
+
+class SystemMap:
+    def __init__(self, prob: ODEProblem, alg: Optional[Tsit5] = None, ensemblealg: Optional[EnsembleB200] = None,
+                 **kwargs):
+        self.prob = prob
+        self.alg = alg
+        self.ensemblealg = ensemblealg if ensemblealg is not None else EnsembleB200()
+        self.kwargs = kwargs  # abstol, reltol, dtmax, maxiters, save_everystep (ignored: end-state only)
+
+
+class ProcessNoiseSystemMap:
+    def __init__(self, prob: SDEProblem, n: int, *args, **kwargs):
+        self.prob = prob
+        self.n = int(n)
+        self.args = args      # (EM(dt),) -- forwarded solve arguments
+        self.kwargs = kwargs  # dt=..., ensemblealg=EnsembleB200(...)
+
+
+class ExpectationProblem:
+    """``ExpectationProblem(sm::SystemMap, g, h, d)`` / ``ExpectationProblem(sm::ProcessNoiseSystemMap, g, h)``.
+
+    ``g``: CUDA source defining ``observable(u_end, p, t_end, out)`` (``g(sol,p)`` restricted to
+    end-state observables); ``h``: CUDA source defining ``hmap``; ``nout`` is the observable's length
+    (the reference learns it from a prototype solve, here the kernel needs it at compile time)."""
+
+    def __init__(self, S, g: str, h: str, d: Optional[GenericDistribution] = None, *, nout: int = 1):
+        self.S, self.g, self.h = S, g, h
+        if isinstance(S, ProcessNoiseSystemMap):
+            if d is not None:
+                raise TypeError("ExpectationProblem(sm::ProcessNoiseSystemMap, g, h) takes no distribution")
+            # problem_types.jl:83: n x Truncated(Normal(), -4, 4)
+            d = GenericDistribution(*[truncated(Normal(), -4.0, 4.0) for _ in range(S.n)])
+            self.params = np.array(S.prob.p, dtype=np.float64).copy()
+        else:
+            if d is None:
+                raise TypeError("ExpectationProblem(sm::SystemMap, g, h, d) needs a distribution")
+            self.params = (np.array(S.prob.u0, dtype=np.float64).copy(), np.array(S.prob.p, dtype=np.float64).copy())
+        self.d = d
+        self.nout = int(nout)
+        self._handle = None
+        self._handle_key = None
+
+    # getters of the reference (problem_types.jl:68-72)
+    def distribution(self): return self.d
+    def mapping(self): return self.S
+    def observable(self): return self.g
+    def input_cov(self): return self.h
+    def parameters(self): return self.params
+
+    # ---- lowering to the C ABI ----
+    def model_spec(self) -> ModelSpec:
+        S = self.S
+        prob = S.prob
+        if isinstance(S, ProcessNoiseSystemMap):
+            ens = S.kwargs.get("ensemblealg", EnsembleB200())
+            alg = next((a for a in S.args if isinstance(a, EM)), None)
+            if alg is None:
+                raise NotImplementedError("the B200 process-noise path implements fixed-step EM(); pass EM(dt) in args")
+            dt = float(S.kwargs.get("dt", alg.dt))
+            if not dt > 0:
+                raise ValueError("EM needs dt > 0")
+            src = prob.f + "\n" + prob.g + "\n" + self.h + "\n" + self.g
+            return ModelSpec(source=src, nstate=len(prob.u0), nparam=len(prob.p), nx=len(self.d), nout=self.nout,
+                             u0=list(prob.u0), p=list(prob.p), tspan=tuple(prob.tspan), solver=_capi.SOLVER_EM,
+                             n_kkl=S.n, dt_fixed=dt, pdf=self.d.table(), fp_mode=FP32 if ens.fp32 else FP64,
+                             devices=ens.devices, block_size=ens.block_size, blocks_per_sm=ens.blocks_per_sm,
+                             refill_threshold=ens.refill_threshold, chunk_points=ens.chunk_points)
+        ens = S.ensemblealg
+        if not isinstance(ens, EnsembleB200):
+            raise TypeError("this package only carries the EnsembleB200 ensemble algorithm (no CPU fallback)")
+        if S.alg is not None and not isinstance(S.alg, Tsit5):
+            raise NotImplementedError("the B200 ODE path implements Tsit5()")
+        kw = dict(S.kwargs)
+        src = prob.f + "\n" + self.h + "\n" + self.g
+        return ModelSpec(source=src, nstate=len(prob.u0), nparam=len(prob.p), nx=len(self.d), nout=self.nout,
+                         u0=list(prob.u0), p=list(prob.p), tspan=tuple(prob.tspan), solver=_capi.SOLVER_TSIT5,
+                         abstol=float(kw.get("abstol", 1e-6)), reltol=float(kw.get("reltol", 1e-3)),
+                         dtmax=float(kw.get("dtmax", 0.0)), maxiters=int(kw.get("maxiters", 100000)),
+                         pdf=self.d.table(), fp_mode=FP32 if ens.fp32 else FP64, devices=ens.devices,
+                         block_size=ens.block_size, blocks_per_sm=ens.blocks_per_sm,
+                         refill_threshold=ens.refill_threshold, chunk_points=ens.chunk_points)
+
+    def handle(self) -> _capi.Handle:
+        spec = self.model_spec()
+        key = repr(spec)
+        if self._handle is None or self._handle_key != key:
+            if self._handle is not None:
+                self._handle.close()
+            self._handle = _capi.Handle(spec)
+            self._handle_key = key
+        return self._handle
+
+    def close(self):
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+
+
+@dataclass
+class ExpectationSolution:
+    u: Any
+    resid: Any
+    original: Any
+
+    def __repr__(self):
+        u = np.asarray(self.u)
+        if u.ndim and u.size > 1:
+            return f"ExpectationSolution(u={u.size}-element {type(self.u).__name__})"
+        return f"ExpectationSolution(u={self.u})"
+
+
+@dataclass(frozen=True)
+class Koopman:
+    sensealg: Any = None
+
+
+@dataclass
+class MonteCarlo:
+    """``MonteCarlo(trajectories)``.  ``seed`` keys the host-generated sample stream (block b is a
+    pure function of (seed, b)); ``samples`` supplies a caller-generated set instead -- the "same
+    host-generated sample set" the CPU arm consumes."""
+    trajectories: int
+    seed: int = 0
+    samples: Any = None
+    block: int = 1 << 20
+
+
+@dataclass(frozen=True)
+class CubatureJLh:
+    """h-adaptive Genz-Malik cubature (Integrals.jl's ``CubatureJLh``; error_norm INDIVIDUAL)."""
+    pass
+
+
+class BatchIntegralFunction:
+    """``BatchIntegralFunction{true}(f!, prototype; max_batch)`` of the reference (expectation.jl:199)."""
+
+    def __init__(self, f, prototype, max_batch):
+        self.f = f
+        self.integrand_prototype = prototype
+        self.max_batch = max_batch
+
+    def __call__(self, dx, x, p=None):
+        return self.f(dx, x, p)
+
+
+def build_integrand(prob: ExpectationProblem, alg: Koopman, mid, p, batch: Optional[int]):
+    """``build_integrand(prob, ::Koopman, mid, p, batch::Integer)`` for SystemMap and
+    ProcessNoiseSystemMap problems (reference src/expectation.jl:169-200, :209-249).
+
+    Returns ``f!(dx, x, p)``: ``x`` is ``dim x npts`` in Julia, i.e. ``(npts, dim)`` C-order here, and
+    ``dx`` is ``(npts, nout)`` -- or ``(npts,)`` for a scalar observable (test/interface.jl:78-98).
+    As in the reference, one prototype trajectory at the domain midpoint is solved up front."""
+    if batch is None:
+        raise NotImplementedError("the unbatched integrand stays on the CPU path of the reference; "
+                                  "pass batch=<int> (reference: 'Batching is required' for process noise)")
+    h = prob.handle()
+    nx, nout = h.spec.nx, h.spec.nout
+
+    def integrand_batch(dx, x, _p=None):
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64)).reshape(-1, nx)
+        out = h.eval_nodes(x, layout=LAYOUT_POINT_MAJOR, weight_by_pdf=True)
+        dx[...] = out.reshape(np.shape(dx))
+        return None
+
+    mid = np.asarray(mid, dtype=np.float64).reshape(1, nx)
+    proto = h.eval_nodes(mid, weight_by_pdf=True)
+    prototype = proto.reshape(1) if nout == 1 else proto.reshape(1, nout)
+    return BatchIntegralFunction(integrand_batch, prototype, batch)
+
+
+def solve(prob: ExpectationProblem, expalg, *, maxiters: int = 1000000, batch: Optional[int] = None,
+          quadalg=None, ireltol: float = 1e-2, iabstol: float = 1e-2, record_batches: Optional[list] = None):
+    """``solve(exprob, Koopman(); maxiters, batch, quadalg, ireltol, iabstol)`` /
+    ``solve(exprob, MonteCarlo(n))`` (reference src/expectation.jl:336-354, :268-325)."""
+    if isinstance(expalg, MonteCarlo):
+        return _solve_montecarlo(prob, expalg)
+    if not isinstance(expalg, Koopman):
+        raise TypeError(f"unknown expectation algorithm {expalg!r}")
+    if quadalg is None:
+        quadalg = CubatureJLh()
+    if not isinstance(quadalg, CubatureJLh):
+        raise NotImplementedError("the batched B200 path is driven by CubatureJLh()")
+    lb, ub = extrema(prob.d)
+    integrand = build_integrand(prob, expalg, (lb + ub) / 2.0, prob.params, batch)
+    nout = prob.nout
+
+    def f(x):
+        dx = np.empty((len(x), nout))
+        integrand(dx, x, prob.params)
+        return dx
+
+    res = hcubature_v(f, lb, ub, fdim=nout, reltol=ireltol, abstol=iabstol, maxevals=maxiters,
+                      max_batch=None, record=record_batches)
+    u = res.u[0] if nout == 1 else res.u
+    resid = res.resid[0] if nout == 1 else res.resid
+    return ExpectationSolution(u, resid, res)
+
+
+def _solve_montecarlo(prob: ExpectationProblem, alg: MonteCarlo):
+    h = prob.handle()
+    n = int(alg.trajectories)
+    nout = prob.nout
+    total = np.zeros(nout)
+    counters = {"nf": 0, "naccept": 0, "nreject": 0, "nfail": 0}
+    if alg.samples is not None:
+        s, _, c = h.reduce_samples(alg.samples, weight_by_pdf=False, npts=n)
+        total += s
+        counters = c
+    else:
+        done, b = 0, 0
+        while done < n:
+            m = min(alg.block, n - done)
+            x = prob.d.rand_block(alg.seed, b, alg.block)[:m] if m < alg.block else prob.d.rand_block(alg.seed, b, alg.block)
+            s, _, c = h.reduce_samples(np.ascontiguousarray(x), weight_by_pdf=False)
+            total += s
+            for k in counters:
+                counters[k] += c[k]
+            done += m
+            b += 1
+    mean = total / n  # mean(sol.u), expectation.jl:293
+    sol = ExpectationSolution(mean[0] if nout == 1 else mean, None, None)
+    sol.counters = counters
+    return sol

@@ -1,0 +1,101 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/b200_expect.h declares,
+cross-compiles models for sm_100a through NVRTC, validates its inputs, and REFUSES to compute without a
+device (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200_expect.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200e_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(sme):
+    L = sme.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/b200_expect.h but not exported"
+    assert sorted(sme._capi.EXPORTS) == names
+    assert L.b200e_abi_version() == 1
+
+
+def test_struct_layout_matches_header(sme):
+    # sizes computed by hand from the header (LP64): catches drift between the ctypes mirror and the C structs
+    assert C.sizeof(sme._capi.PdfDim) == 40
+    assert C.sizeof(sme._capi.Counters) == 32
+    assert C.sizeof(sme._capi.CallStats) == 64
+    assert C.sizeof(sme._capi.Model) == 160
+
+
+def test_compile_check_all_builtin_models_for_sm100a(sme, tmp_path):
+    for name in sme.models.BUILTIN:
+        for fp in (0, 1):
+            spec = sme.models.builtin(name, fp_mode=fp, cache_dir=str(tmp_path))
+            nbytes, log = sme.compile_check(spec)
+            assert nbytes > 10000
+            assert "sm_100a" in log and "b200e_reduce" in log and "b200e_nodes" in log
+            assert "0 bytes spill stores" in log and "bytes spill stores" in log
+            assert not re.search(r"[1-9]\d* bytes spill", log), log
+            # second call is served from the cubin cache
+            n2, log2 = sme.compile_check(spec)
+            assert n2 == nbytes and "loaded from cache" in log2
+
+
+def test_compile_error_is_reported_with_log(sme):
+    bad = sme.models.builtin("linear2", cache_dir="")
+    bad = bad.replace(source=bad.source.replace("du[0] = u[1];", "du[0] = undefined_symbol;"))
+    with pytest.raises(sme.B200Error) as e:
+        sme.compile_check(bad)
+    assert e.value.code == sme._capi.ERR_COMPILE and "undefined_symbol" in str(e.value)
+
+
+@pytest.mark.parametrize("field,value", [("nstate", 0), ("nstate", 17), ("nx", 33), ("nout", 0), ("solver", 7),
+                                         ("fp_mode", 3), ("block_size", 48), ("tspan", (1.0, 1.0)),
+                                         ("abstol", -1.0), ("refill_threshold", 40)])
+def test_invalid_models_are_rejected(sme, field, value):
+    spec = sme.models.builtin("linear2").replace(**{field: value})
+    with pytest.raises(sme.B200Error) as e:
+        sme.compile_check(spec)
+    assert e.value.code == sme._capi.ERR_INVALID
+
+
+def test_invalid_pdf_and_em_settings(sme):
+    spec = sme.models.builtin("linear2")
+    with pytest.raises(sme.B200Error):
+        sme.compile_check(spec.replace(pdf=[(1, 3.0, 2.0, 0, 1), (3, 0.0, 6.0, 3.0, 1.0)]))
+    with pytest.raises(sme.B200Error):
+        sme.compile_check(spec.replace(pdf=[(1, 1.0, 10.0, 0, 1), (3, 0.0, 6.0, 3.0, -1.0)]))
+    em = sme.models.builtin("gbm4")
+    with pytest.raises(sme.B200Error):
+        sme.compile_check(em.replace(dt_fixed=0.0))
+    with pytest.raises(sme.B200Error):
+        sme.compile_check(em.replace(n_kkl=0))
+
+
+def test_no_cpu_fallback(sme):
+    """On a machine without a CUDA device every compute entry point fails loudly."""
+    if sme.device_count() > 0:
+        pytest.skip("a CUDA device is visible here")
+    with pytest.raises(sme.B200Error) as e:
+        sme.Handle(sme.models.builtin("linear2"))
+    assert e.value.code == sme._capi.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+    with pytest.raises(sme.B200Error):
+        sme.measure_fma_peak()
+    with pytest.raises(sme.B200Error):
+        sme.PinnedArray((4, 2))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "scimlexpectations.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "expect_oracle" not in text, f

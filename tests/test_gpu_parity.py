@@ -1,0 +1,328 @@
+"""GPU (-m gpu): parity of the CUDA path against the oracle, called through the C ABI.
+
+Tolerances.  Integer bookkeeping (RHS evaluations, accepted / rejected steps, failed trajectories,
+per-point attempted steps, output column <-> input column) is BIT-EXACT.  Floating point: expectations
+(sums over a batch) within 1e-8 relative (north_star); observed ~1e-11.  Per-node values: the kernel and
+the oracle run the same algorithm with different rounding (CUDA log/exp vs glibc pow, FMA contraction),
+and the Hairer-Wanner initial-step heuristic amplifies rounding noise by ~1e5 (cancellation in
+f(u0 + dt0 f0) - f0), so individual trajectories of the nonlinear problems agree to ~1e-7 worst case and
+~1e-12 in the median -- the same spread the oracle shows against itself when recompiled without FMA
+contraction ("Parity").  Tests assert: median <= 1e-10, max <= 2e-6 relative to the batch scale.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from tests.sampling_util import sample_points
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "oracle_vectors.npz"))
+README = json.load(open(os.path.join(HERE, "golden", "readme_linear2.json")))
+ALL = ["linear2", "lotka_volterra", "lorenz63", "decay1", "oscillator_noise", "gbm4"]
+ODE = ["linear2", "lotka_volterra", "lorenz63", "decay1"]
+
+
+def _node_err(dx, ref):
+    scale = np.abs(ref).max(axis=0, keepdims=True) + 1e-300
+    e = np.abs(dx - ref) / scale
+    return float(np.median(e)), float(e.max())
+
+
+def _n(name, n):
+    return n if name in ODE else max(64, n // 16)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_nodes_mode_matches_oracle(gpu, name):
+    n = _n(name, 20000)
+    x = sample_points(name, n, seed=1)
+    orc = oracle.OracleProblem.builtin(name)
+    ref, cref, sref = orc.eval_nodes(x, weight_by_pdf=True, want_steps=True)
+    with gpu.Handle(gpu.models.builtin(name)) as h:
+        dx, steps = h.eval_nodes(x, weight_by_pdf=True, want_steps=True)
+        c = h.last_counters()
+        st = h.last_stats()
+    assert c == cref                      # nf / naccept / nreject / nfail bit-exact
+    assert np.array_equal(steps, sref)    # per-point attempted steps bit-exact
+    med, mx = _node_err(dx, ref)
+    assert med <= 1e-10 and mx <= 2e-6, (name, med, mx)
+    assert st["launches"] >= 1 and st["local_bytes_per_thread"] == 0
+    # unweighted (MonteCarlo output_func, expectation.jl:282)
+    with gpu.Handle(gpu.models.builtin(name)) as h:
+        dxu = h.eval_nodes(x, weight_by_pdf=False)
+    refu, _ = orc.eval_nodes(x, weight_by_pdf=False)
+    med, mx = _node_err(dxu, refu)
+    assert med <= 1e-10 and mx <= 2e-6, (name, med, mx)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_reduce_mode_matches_oracle(gpu, name):
+    n = _n(name, 200000)
+    x = sample_points(name, n, seed=2)
+    orc = oracle.OracleProblem.builtin(name)
+    so, s2o, co = orc.reduce_samples(x)
+    with gpu.Handle(gpu.models.builtin(name)) as h:
+        s, s2, c = h.reduce_samples(x)
+        # pdf-weighted reduction (the Koopman accumulators of SURVEY.md 8f rank 1)
+        sw, s2w, cw = h.reduce_samples(x, weight_by_pdf=True)
+    assert c == co and cw == co
+    assert np.max(np.abs(s - so) / np.abs(so)) < 1e-8          # north_star tolerance
+    assert np.max(np.abs(s2 - s2o) / np.abs(s2o)) < 1e-8
+    swo, s2wo, _ = orc.reduce_samples(x, weight_by_pdf=True)
+    assert np.max(np.abs(sw - swo) / np.abs(swo)) < 1e-8
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_golden_fixture(gpu, name):
+    """tests/golden/oracle_vectors.npz (written by tests/golden/make_golden.py)."""
+    x = GOLD[f"{name}_x"]
+    with gpu.Handle(gpu.models.builtin(name)) as h:
+        dx, steps = h.eval_nodes(x, weight_by_pdf=True, want_steps=True)
+        c = h.last_counters()
+        s, s2, c2 = h.reduce_samples(x)
+    assert np.array_equal(steps, GOLD[f"{name}_steps"])
+    assert [c["nf"], c["naccept"], c["nreject"], c["nfail"]] == GOLD[f"{name}_counters"].tolist()
+    med, mx = _node_err(dx, GOLD[f"{name}_dx"])
+    assert med <= 1e-10 and mx <= 2e-6
+    assert np.allclose(s, GOLD[f"{name}_sum"], rtol=1e-8) and np.allclose(s2, GOLD[f"{name}_sumsq"], rtol=1e-8)
+
+
+def test_layouts_pointer_kinds_and_chunking_agree(gpu):
+    """point-major vs SoA, pageable vs pinned vs device-resident input, one launch vs many chunks:
+    same per-node values bit for bit (a node's output depends on its own column only) and the same
+    integer counters; sums agree to rounding."""
+    name = "lorenz63"
+    n = 50001
+    x = sample_points(name, n, seed=4)
+    with gpu.Handle(gpu.models.builtin(name)) as h:
+        base = h.eval_nodes(x)
+        cbase = h.last_counters()
+        soa = h.eval_nodes(np.ascontiguousarray(x.T), layout=1)
+        assert np.array_equal(soa.T, base) and h.last_counters() == cbase
+        pin = h.pinned(x.shape)
+        pin.array[...] = x
+        assert np.array_equal(h.eval_nodes(pin), base)
+        dev = h.device_array(x.shape).upload(x)
+        out = h.device_array((n, 3))
+        h.eval_nodes(dev, npts=n, out=out)
+        assert np.array_equal(out.download(), base) and h.last_stats()["h2d_bytes"] == 0
+        s1, q1, c1 = h.reduce_samples(dev, npts=n)
+        s0, q0, c0 = h.reduce_samples(x)
+        assert c1 == c0 == cbase and np.allclose(s1, s0, rtol=1e-13)
+        dev.free(); out.free(); pin.free()
+    # a ragged chunk size that forces many ring-slot reuses
+    with gpu.Handle(gpu.models.builtin(name, chunk_points=777)) as h:
+        assert np.array_equal(h.eval_nodes(x), base)
+        assert h.last_counters() == cbase and h.last_stats()["launches"] >= n // 777
+        assert np.array_equal(h.eval_nodes(np.ascontiguousarray(x.T), layout=1).T, base)
+        s2_, q2_, c2_ = h.reduce_samples(x)
+        assert c2_ == cbase and np.allclose(s2_, s0, rtol=1e-13)
+
+
+@pytest.mark.parametrize("block,per_sm,refill", [(32, 1, 1), (64, 2, 8), (128, 4, 16), (256, 2, 32), (128, 0, 24)])
+def test_results_do_not_depend_on_launch_shape(gpu, block, per_sm, refill):
+    """Sample-index bookkeeping: whatever the grid / refill policy, node i gets the same value and the
+    counters the same integers."""
+    name = "lotka_volterra"
+    x = sample_points(name, 30011, seed=6)
+    with gpu.Handle(gpu.models.builtin(name)) as h:
+        base, sbase = h.eval_nodes(x, want_steps=True)
+        cbase = h.last_counters()
+    spec = gpu.models.builtin(name, block_size=block, blocks_per_sm=per_sm, refill_threshold=refill)
+    with gpu.Handle(spec) as h:
+        dx, steps = h.eval_nodes(x, want_steps=True)
+        assert np.array_equal(dx, base) and np.array_equal(steps, sbase) and h.last_counters() == cbase
+        s, s2, c = h.reduce_samples(x)
+        assert c == cbase
+
+
+def test_edge_cases(gpu):
+    orc = oracle.OracleProblem.builtin("linear2")
+    with gpu.Handle(gpu.models.builtin("linear2")) as h:
+        # empty batch
+        e = h.eval_nodes(np.zeros((0, 2)))
+        assert e.shape == (0, 2) and h.last_counters() == {"nf": 0, "naccept": 0, "nreject": 0, "nfail": 0}
+        s, s2, c = h.reduce_samples(np.zeros((0, 2)))
+        assert np.all(s == 0) and c["nf"] == 0
+        # single point, and sizes around warp / block boundaries
+        for n in (1, 31, 32, 33, 127, 129):
+            x = sample_points("linear2", n, seed=8)
+            ref, cr = orc.eval_nodes(x)
+            dx = h.eval_nodes(x)
+            assert h.last_counters() == cr and np.allclose(dx, ref, rtol=1e-9, atol=1e-300)
+        # points outside the support: weight exactly 0 (pdf = exp(-Inf)), still solved and counted
+        x = np.array([[0.5, 3.0], [5.0, 6.5], [5.0, 3.0]])
+        dx = h.eval_nodes(x, weight_by_pdf=True)
+        assert np.all(dx[:2] == 0.0) and np.all(dx[2] != 0.0)
+        assert h.last_counters() == orc.eval_nodes(x)[1]
+        # bad arguments are status codes, not crashes
+        with pytest.raises(gpu.B200Error):
+            h.eval_nodes(x, layout=5)
+    # weight requested without a pdf table
+    with gpu.Handle(gpu.models.builtin("linear2", pdf=None)) as h:
+        with pytest.raises(gpu.B200Error):
+            h.eval_nodes(np.ones((4, 2)), weight_by_pdf=True)
+        assert h.eval_nodes(np.ones((4, 2)), weight_by_pdf=False).shape == (4, 2)
+
+
+def test_failed_trajectories_are_counted_like_the_oracle(gpu):
+    """maxiters exhaustion / non-finite states: retcodes in the reference, nfail here; g still applied."""
+    x = sample_points("lotka_volterra", 1000, seed=1)
+    orc = oracle.OracleProblem.builtin("lotka_volterra", maxiters=7)
+    ref, cr, sr = orc.eval_nodes(x, weight_by_pdf=False, want_steps=True)
+    with gpu.Handle(gpu.models.builtin("lotka_volterra", maxiters=7)) as h:
+        dx, steps = h.eval_nodes(x, weight_by_pdf=False, want_steps=True)
+        c = h.last_counters()
+    assert c == cr and c["nfail"] == 1000 and np.array_equal(steps, sr)
+    assert np.allclose(dx, ref, rtol=1e-6)
+    # a blow-up: du = u^2 from u0 = x0 >= 1 over (0, 3) leaves the finite range -> every trajectory fails
+    src = """
+B200E_FN void rhs(real* du, const real* u, const real* p, real t) { du[0] = u[0] * u[0]; du[1] = B200E_REAL(0.0); }
+B200E_FN void hmap(const real* x, const real* a, const real* b, real* u0, real* p) { u0[0] = x[0]; u0[1] = x[1]; }
+B200E_FN void observable(const real* u, const real* p, real t, real* out) { out[0] = u[0]; out[1] = u[1]; }
+"""
+    xs = sample_points("linear2", 500, seed=3)
+    o2 = oracle.OracleProblem.from_source(src, nstate=2, nparam=2, nx=2, nout=2, u0=[1, 1], p=[1, 2], tspan=(0, 3))
+    _, c2r = o2.eval_nodes(xs, weight_by_pdf=False)
+    with gpu.Handle(gpu.models.builtin("linear2", source=src, pdf=None)) as h:
+        h.eval_nodes(xs, weight_by_pdf=False)
+        c2 = h.last_counters()
+    # near the singularity rounding decides individual accept/reject outcomes, so only the failure
+    # bookkeeping is compared here, not the step counts
+    assert c2["nfail"] == c2r["nfail"] == 500
+
+
+def test_tolerances_are_forwarded(gpu):
+    """SystemMap kwargs reach the solver (system_utils.jl:42-53): tighter tolerances -> more steps, and
+    the result converges to exp(A*3) x."""
+    from scipy.linalg import expm
+    x = sample_points("linear2", 2000, seed=5)
+    E = expm(np.array([[0.0, 1.0], [-1.0, -2.0]]) * 3.0)
+    for tol, bound in ((1e-6, 1e-5), (1e-10, 1e-9)):
+        orc = oracle.OracleProblem.builtin("linear2", abstol=tol, reltol=tol)
+        with gpu.Handle(gpu.models.builtin("linear2", abstol=tol, reltol=tol)) as h:
+            dx = h.eval_nodes(x, weight_by_pdf=False)
+            assert h.last_counters() == orc.eval_nodes(x, weight_by_pdf=False)[1]
+        assert np.max(np.abs(dx - x @ E.T)) < bound
+
+
+def test_fp32_mode(gpu):
+    """Optional FP32 state arithmetic (north_star): accumulation stays FP64; agreement with the FP64
+    oracle at single-precision level."""
+    for name, tol in (("linear2", 2e-4), ("lorenz63", 2e-3)):
+        x = sample_points(name, 20000, seed=7)
+        so, s2o, co = oracle.OracleProblem.builtin(name).reduce_samples(x)
+        with gpu.Handle(gpu.models.builtin(name, fp_mode=1)) as h:
+            s, s2, c = h.reduce_samples(x)
+        assert np.max(np.abs(s - so) / np.abs(so)) < tol
+        assert c["nfail"] == 0 and abs(c["naccept"] - co["naccept"]) < 0.02 * co["naccept"]
+
+
+def test_full_size_properties_linear2_1e7(gpu):
+    """BASELINE configs[1] at full size (10^7 samples).  Size-independent properties:
+    (1) the ODE is linear, so mean(u(T)) = Phi * mean(x) with Phi from two basis trajectories;
+    (2) chunk invariance: 10 chunked calls sum to the single-launch result;
+    (3) counters obey nf = 3n + 6 (naccept + nreject) exactly; no failures;
+    (4) a 2^18-sample prefix agrees with the oracle to 1e-8 with bit-exact counters."""
+    n = 10_000_000
+    x = sample_points("linear2", n, seed=20261019)
+    with gpu.Handle(gpu.models.builtin("linear2")) as h:
+        d = h.device_array(x.shape).upload(x)
+        s, s2, c = h.reduce_samples(d, npts=n)
+        basis = h.eval_nodes(np.eye(2), weight_by_pdf=False)          # rows: Phi e1, Phi e2 (numerical)
+        parts = np.zeros(2)
+        cc = {"nf": 0, "naccept": 0, "nreject": 0, "nfail": 0}
+        for k in range(10):
+            sk, _, ck = h.reduce_samples(x[k * 1_000_000:(k + 1) * 1_000_000])
+            parts += sk
+            for key in cc:
+                cc[key] += ck[key]
+        d.free()
+    assert c == cc and np.allclose(parts, s, rtol=1e-12)
+    assert c["nfail"] == 0 and c["nf"] == 3 * n + 6 * (c["naccept"] + c["nreject"])
+    # numerical flow map is linear in u0 only up to the adaptive step selection: agreement ~ODE error
+    assert np.allclose(s / n, x.mean(axis=0) @ basis, rtol=0, atol=5e-4)
+    assert np.allclose(s / n, README["analytical"], rtol=5e-3)       # MC error ~ 1/sqrt(1e7)
+    m = 1 << 18
+    so, s2o, co = oracle.OracleProblem.builtin("linear2").reduce_samples(x[:m])
+    with gpu.Handle(gpu.models.builtin("linear2")) as h:
+        sp, s2p, cp = h.reduce_samples(x[:m])
+    assert cp == co and np.max(np.abs(sp - so) / np.abs(so)) < 1e-8 and np.max(np.abs(s2p - s2o) / np.abs(s2o)) < 1e-8
+
+
+def test_readme_koopman_through_public_api(gpu):
+    """reference README.md:28-78 end to end through the mirrored API on the GPU: same node batches as the
+    oracle-driven run (17, 34, 68 nodes), u and resid within 1e-8 relative of the CPU result, and the
+    published digits reproduced."""
+    m = gpu.models
+    prob = gpu.ODEProblem(m._LINEAR2_RHS, [1.0, 1.0], (0.0, 3.0), [1.0, 2.0])
+    smap = gpu.SystemMap(prob, gpu.Tsit5(), gpu.EnsembleB200(), save_everystep=False)
+    gd = gpu.GenericDistribution(gpu.Uniform(1, 10), gpu.truncated(gpu.Normal(3, 1), 0, 6))
+    ex = gpu.ExpectationProblem(smap, m.observable_components([0, 1]), m.hmap_scatter(u0_from_x=[(0, 0), (1, 1)]), gd, nout=2)
+    rec = []
+    sol = gpu.solve(ex, gpu.Koopman(), batch=20, quadalg=gpu.CubatureJLh(), ireltol=1e-3, iabstol=1e-3, record_batches=rec)
+    orc = oracle.OracleProblem.builtin("linear2")
+    rec_cpu = []
+    ref = gpu.hcubature_v(lambda x: orc.eval_nodes(x, weight_by_pdf=True)[0], [1.0, 0.0], [10.0, 6.0], fdim=2,
+                          reltol=1e-3, abstol=1e-3, record=rec_cpu)
+    assert [len(b) for b in rec] == [17, 34, 68] and all(np.array_equal(a, b) for a, b in zip(rec, rec_cpu))
+    assert np.max(np.abs(sol.u - ref.u) / np.abs(ref.u)) < 1e-8
+    assert np.max(np.abs(sol.resid - ref.resid) / np.abs(ref.resid)) < 1e-8
+    assert np.allclose(sol.u, README["koopman_u"], rtol=0, atol=2e-9)
+    assert np.allclose(sol.resid, README["koopman_resid"], rtol=0, atol=1e-10)
+    # MonteCarlo(10000) at the reference's own tolerance (test/solve.jl:81)
+    mc = gpu.solve(ex, gpu.MonteCarlo(10000, seed=3))
+    assert np.allclose(mc.u, README["analytical"], rtol=1e-2) and mc.resid is None
+    # batch shape contract (test/interface.jl:78-98): dim x npts in, nout x npts (or npts) out
+    f = gpu.build_integrand(ex, gpu.Koopman(), [5.5, 3.0], ex.params, 5)
+    y = np.tile([5.5, 3.0], (5, 1))
+    dy = np.empty((5, 2))
+    f(dy, y, ex.params)
+    assert np.allclose(dy, orc.eval_nodes(y)[0], rtol=1e-9) and f.integrand_prototype.shape == (1, 2)
+    ex1 = gpu.ExpectationProblem(smap, m.observable_components([0]), ex.h, gd, nout=1)
+    f1 = gpu.build_integrand(ex1, gpu.Koopman(), [5.5, 3.0], ex1.params, 5)
+    dy1 = np.empty(5)
+    f1(dy1, y, ex1.params)
+    assert np.allclose(dy1, dy[:, 0]) and f1.integrand_prototype.shape == (1,)
+    ex.close(); ex1.close()
+
+
+def test_lotka_volterra_koopman_batched(gpu):
+    """BASELINE configs[2]: LV with 4 uncertain parameters, batched Genz-Malik rounds (57 nodes/region).
+    GPU and CPU consume the same node batches; u and resid agree to 1e-8 as long as the refinement
+    sequences coincide (they are compared batch by batch)."""
+    orc = oracle.OracleProblem.builtin("lotka_volterra")
+    lb, ub = [1.0, 0.5, 2.0, 0.5], [2.0, 1.5, 4.0, 1.5]
+    rec_c, rec_g = [], []
+    ref = gpu.hcubature_v(lambda x: orc.eval_nodes(x, weight_by_pdf=True)[0], lb, ub, fdim=1, reltol=1e-3, abstol=1e-3,
+                          maxevals=200000, record=rec_c)
+    with gpu.Handle(gpu.models.builtin("lotka_volterra")) as h:
+        got = gpu.hcubature_v(lambda x: h.eval_nodes(x, weight_by_pdf=True), lb, ub, fdim=1, reltol=1e-3, abstol=1e-3,
+                              maxevals=200000, record=rec_g)
+    assert [len(b) for b in rec_g] == [len(b) for b in rec_c] and all(len(b) % 57 == 0 for b in rec_g)
+    assert all(np.array_equal(a, b) for a, b in zip(rec_g, rec_c))
+    assert abs(got.u[0] - ref.u[0]) / abs(ref.u[0]) < 1e-8
+    assert abs(got.resid[0] - ref.resid[0]) / abs(ref.resid[0]) < 1e-6   # resid is a difference of two rules
+    assert got.nevals == ref.nevals and got.converged == ref.converged
+
+
+def test_process_noise_koopman_vs_montecarlo(gpu):
+    """test/processnoise.jl:9-26 with fixed-step EM in place of LambaEM: MonteCarlo(10^6) of the GBM
+    f=g=u, u0=1:4 against the closed form E[u(1)] = u0 * E[exp(1 + W8(1))] at the reference's rtol=1e-2."""
+    m = gpu.models
+    f, g = m._GBM.split("B200E_FN void diffusion")
+    sde = gpu.SDEProblem(f, "B200E_FN void diffusion" + g, [1.0, 2.0, 3.0, 4.0], (0.0, 1.0), [])
+    pn = gpu.ProcessNoiseSystemMap(sde, 8, gpu.EM(), dt=1 / 1024)
+    ex = gpu.ExpectationProblem(pn, m.observable_components([0, 1, 2, 3]), m.hmap_scatter(z_from_x=[(k, k) for k in range(8)]), nout=4)
+    mc = gpu.solve(ex, gpu.MonteCarlo(1_000_000, seed=5))
+    # W8(1) = sum_k Z_k c_k with c_k = sqrt(2) sin((k-1/2)pi)/((k-1/2)pi); Z_k ~ tN(0,1;-4,4) ~ N(0,1)
+    ck = np.array([np.sqrt(2.0) * np.sin((k - 0.5) * np.pi) / ((k - 0.5) * np.pi) for k in range(1, 9)])
+    want = np.array([1.0, 2.0, 3.0, 4.0]) * np.exp(1.0 + 0.5 * np.sum(ck ** 2))
+    assert np.allclose(mc.u, want, rtol=1e-2), (mc.u, want)
+    assert mc.counters["nfail"] == 0 and mc.counters["nf"] == 1_000_000 * 1024
+    ex.close()

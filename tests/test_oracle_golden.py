@@ -1,0 +1,197 @@
+"""CPU: pins the oracle (CPU restatement of the reference path) against every golden vector and
+known answer the reference holds for this path, and against an independent
+pure-Python restatement."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+from scipy import stats
+from scipy.linalg import expm
+
+import oracle
+from tests import ref_numpy
+from tests.sampling_util import sample_points
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+README = json.load(open(os.path.join(HERE, "golden", "readme_linear2.json")))
+GOLD = np.load(os.path.join(HERE, "golden", "oracle_vectors.npz"))
+
+
+def _cubature():
+    import scimlexpectations_jl_b200 as sme  # host-side driver only; nothing here touches the GPU library
+    return sme.cubature.hcubature_v
+
+
+def test_tsit5_tableau_order_conditions():
+    A = np.zeros((7, 7))
+    for i, row in enumerate(ref_numpy.A):
+        A[i, :len(row)] = row
+    c = np.array(ref_numpy.C)
+    b = A[6]
+    bt = np.array(ref_numpy.BTILDE)
+    assert np.allclose(A.sum(axis=1), c, atol=1e-15)
+    # order conditions through order 4 for b (a subset of the order-5 set; all must vanish)
+    assert abs(b.sum() - 1) < 1e-15
+    assert abs(b @ c - 1 / 2) < 1e-15
+    assert abs(b @ c**2 - 1 / 3) < 1e-15
+    assert abs(b @ (A @ c) - 1 / 6) < 1e-15
+    assert abs(b @ c**3 - 1 / 4) < 1e-15
+    assert abs((b * c) @ (A @ c) - 1 / 8) < 1e-15
+    assert abs(b @ (A @ c**2) - 1 / 12) < 1e-15
+    assert abs(b @ (A @ (A @ c)) - 1 / 24) < 1e-15
+    assert abs(b @ c**4 - 1 / 5) < 1e-15
+    # btilde = b - bhat annihilates the 4th-order conditions of the embedded method
+    for v in (np.ones(7), c, c**2, c**3, A @ c):
+        assert abs(bt @ v) < 2e-15
+
+
+def test_oracle_matches_independent_python_restatement():
+    for name, rhs, npts in (("linear2", ref_numpy.linear2_rhs, 12), ("lotka_volterra", ref_numpy.lv_rhs, 12),
+                            ("lorenz63", ref_numpy.lorenz_rhs, 12)):
+        x = sample_points(name, npts, seed=5)
+        orc = oracle.OracleProblem.builtin(name)
+        dx, c, steps = orc.eval_nodes(x, weight_by_pdf=False, want_steps=True)
+        tot = [0, 0, 0]
+        for i in range(npts):
+            if name == "linear2":
+                u, nf, na, nr = ref_numpy.tsit5(rhs, x[i], None, 0.0, 3.0)
+                got = u
+            elif name == "lotka_volterra":
+                u, nf, na, nr = ref_numpy.tsit5(rhs, [1.0, 1.0], x[i], 0.0, 10.0)
+                got = u[:1]
+            else:
+                u, nf, na, nr = ref_numpy.tsit5(rhs, x[i, 3:], x[i, :3], 0.0, 1.0)
+                got = u
+            assert na + nr == steps[i]
+            # identical algorithm, different rounding: the initial-step heuristic amplifies rounding
+            # noise (cancellation in f1 - f0), so trajectories agree to ~1e-8, most to 1e-12
+            assert np.allclose(got, dx[i], rtol=2e-7, atol=1e-12), (name, i, got, dx[i])
+            tot[0] += nf; tot[1] += na; tot[2] += nr
+        assert (c["nf"], c["naccept"], c["nreject"]) == tuple(tot)
+
+
+def test_linear2_tight_tolerance_matches_matrix_exponential():
+    orc = oracle.OracleProblem.builtin("linear2", abstol=1e-13, reltol=1e-13)
+    x = sample_points("linear2", 16, seed=2)
+    dx, _ = orc.eval_nodes(x, weight_by_pdf=False)
+    E = expm(np.array([[0.0, 1.0], [-1.0, -2.0]]) * 3.0)
+    assert np.allclose(dx, x @ E.T, rtol=0, atol=5e-12)
+
+
+def test_readme_golden_vector_koopman():
+    """reference README.md:57-78: solve(exprob, Koopman(); quadalg=CubatureJLh(), ireltol=1e-3, iabstol=1e-3).
+    Oracle integrand + restated hcubature_v reproduce the published digits (to ~4e-10: the residual is
+    the power-function / FMA difference between OrdinaryDiffEq's build and this restatement)."""
+    orc = oracle.OracleProblem.builtin("linear2")
+    r = _cubature()(lambda x: orc.eval_nodes(x, weight_by_pdf=True)[0], [1.0, 0.0], [10.0, 6.0], fdim=2,
+                    reltol=1e-3, abstol=1e-3)
+    assert r.converged
+    assert np.allclose(r.u, README["koopman_u"], rtol=0, atol=2e-9), r.u - np.array(README["koopman_u"])
+    assert np.allclose(r.resid, README["koopman_resid"], rtol=0, atol=1e-10), r.resid
+    assert r.batch_sizes == [17, 34, 68]
+    # and the analytical value exp(A*3) E[u0] (README.md:50-55) within the ODE discretisation error
+    assert np.allclose(r.u, README["analytical"], rtol=0, atol=5e-5)
+
+
+def test_readme_analytical_value():
+    E = expm(np.array([[0.0, 1.0], [-1.0, -2.0]]) * 3.0)
+    m2 = stats.truncnorm(-3.0, 3.0, loc=3.0, scale=1.0).mean()
+    assert np.allclose(E @ np.array([5.5, m2]), README["analytical"], rtol=0, atol=1e-12)
+
+
+def test_montecarlo_linear2_within_reference_test_tolerance():
+    """test/solve.jl:55, :81: MonteCarlo(10000) vs analytical at rtol=1e-2."""
+    orc = oracle.OracleProblem.builtin("linear2")
+    x = sample_points("linear2", 10000, seed=1)
+    s, s2, c = orc.reduce_samples(x)
+    assert np.allclose(s / len(x), README["analytical"], rtol=1e-2)
+    assert c["nfail"] == 0 and c["nf"] == 3 * len(x) + 6 * (c["naccept"] + c["nreject"])
+
+
+def test_decay_variance_known_answer():
+    """test/solve.jl:137-173: du=-0.5u, u0~truncated(Normal(1,0.1),0.5,1.5), tspan (0,2):
+    Var = Var(u0) e^{-2}; Koopman within 1e-3, first central moment ~ 0."""
+    src = """
+B200E_FN void rhs(real* du, const real* u, const real* p, real t) { du[0] = -0.5 * u[0]; }
+B200E_FN void hmap(const real* x, const real* u0n, const real* pn, real* u0, real* p) { u0[0] = x[0]; }
+B200E_FN void observable(const real* u, const real* p, real t, real* out) { out[0] = u[0]; out[1] = u[0]*u[0]; }
+"""
+    orc = oracle.OracleProblem.from_source(src, nstate=1, nparam=0, nx=1, nout=2, u0=[1.0], p=[], tspan=(0.0, 2.0),
+                                           pdf=[(oracle.PDF_TRUNCNORMAL, 0.5, 1.5, 1.0, 0.1)])
+    r = _cubature()(lambda x: orc.eval_nodes(x, weight_by_pdf=True)[0], [0.5], [1.5], fdim=2, reltol=1e-8, abstol=1e-10)
+    var = r.u[1] - r.u[0] ** 2
+    tn = stats.truncnorm(-5.0, 5.0, loc=1.0, scale=0.1)
+    assert abs(var - tn.var() * math.exp(-2.0)) < 1e-3 * tn.var()
+    assert abs(r.u[0] - tn.mean() * math.exp(-1.0)) < 1e-4
+    # builtin decay1 agrees with the from_source model
+    b = oracle.OracleProblem.builtin("decay1")
+    x = sample_points("decay1", 64, seed=3)
+    assert np.array_equal(b.eval_nodes(x)[0][:, 0], orc.eval_nodes(x)[0][:, 0])
+
+
+def test_logpdf_against_scipy():
+    orc = oracle.OracleProblem.builtin("linear2")
+    for x in ([5.0, 3.0], [1.0, 0.0], [10.0, 6.0], [2.5, 4.75]):
+        want = stats.uniform(1, 9).logpdf(x[0]) + stats.truncnorm(-3, 3, loc=3, scale=1).logpdf(x[1])
+        assert abs(orc.logpdf(x) - want) < 1e-13
+    for x in ([0.5, 3.0], [5.0, 6.5], [11.0, -1.0]):
+        assert orc.logpdf(x) == -math.inf
+    # outside the support the weighted integrand is exactly zero (pdf = exp(-Inf))
+    dx, _ = orc.eval_nodes(np.array([[0.5, 3.0], [5.0, 6.5]]), weight_by_pdf=True)
+    assert np.all(dx == 0.0)
+    orc.set_pdf([(oracle.PDF_NORMAL, -math.inf, math.inf, 1.0, 2.0), (oracle.PDF_NONE, 0, 0, 0, 1)])
+    assert abs(orc.logpdf([0.3, 99.0]) - stats.norm(1.0, 2.0).logpdf(0.3)) < 1e-14
+
+
+def test_kkl_series_and_em_closed_form():
+    """src/expectation.jl:217-220 series; GBM f=g=u driven by the smooth KKL path converges to
+    u0 exp(t + W(t)) as dt -> 0 (first order)."""
+    import ctypes as C
+    z = np.array([0.3, -1.2, 0.7, 0.1, -0.4, 2.0, -0.9, 0.05])
+    t = 0.7
+    want = math.sqrt(2.0) * sum(z[k] * math.sin((k + 0.5) * math.pi * t) / ((k + 0.5) * math.pi) for k in range(8))
+    got = oracle.lib().orc_kkl_w(z.ctypes.data_as(C.POINTER(C.c_double)), 8, t)
+    assert abs(got - want) < 1e-15
+    w1 = math.sqrt(2.0) * sum(z[k] * math.sin((k + 0.5) * math.pi) / ((k + 0.5) * math.pi) for k in range(8))
+    exact = np.array([1.0, 2.0, 3.0, 4.0]) * math.exp(1.0 + w1)
+    errs = []
+    for dt in (1 / 256, 1 / 1024):
+        orc = oracle.OracleProblem.builtin("gbm4", dt_fixed=dt)
+        dx, c = orc.eval_nodes(z[None, :], weight_by_pdf=False)
+        assert c["nf"] == round(1 / dt)
+        errs.append(np.max(np.abs(dx[0] - exact) / exact))
+    assert errs[1] < 5e-3 and 3.0 < errs[0] / errs[1] < 5.0, errs
+
+
+def test_golden_fixture_reproduced_by_oracle():
+    """tests/golden/oracle_vectors.npz was written by tests/golden/make_golden.py; the oracle built on
+    this machine must reproduce it (same sources, same flags)."""
+    for name in ("linear2", "lotka_volterra", "lorenz63", "decay1", "oscillator_noise", "gbm4"):
+        x = GOLD[f"{name}_x"]
+        orc = oracle.OracleProblem.builtin(name)
+        dx, c, steps = orc.eval_nodes(x, weight_by_pdf=True, want_steps=True)
+        assert np.array_equal(steps, GOLD[f"{name}_steps"])
+        assert [c["nf"], c["naccept"], c["nreject"], c["nfail"]] == GOLD[f"{name}_counters"].tolist()
+        assert np.allclose(dx, GOLD[f"{name}_dx"], rtol=1e-12, atol=0)
+        s, s2, _ = orc.reduce_samples(x)
+        assert np.allclose(s, GOLD[f"{name}_sum"], rtol=1e-13) and np.allclose(s2, GOLD[f"{name}_sumsq"], rtol=1e-13)
+
+
+def test_oracle_layouts_threads_and_edge_cases():
+    orc = oracle.OracleProblem.builtin("lorenz63")
+    x = sample_points("lorenz63", 1000, seed=9)
+    dx0, c0 = orc.eval_nodes(x, layout=0)
+    dx1, c1 = orc.eval_nodes(np.ascontiguousarray(x.T), layout=1)
+    assert np.array_equal(dx0, dx1.T) and c0 == c1
+    s1, q1, cc1 = orc.reduce_samples(x, nthreads=1)
+    s8, q8, cc8 = orc.reduce_samples(x, nthreads=8)
+    assert np.array_equal(s1, s8) and np.array_equal(q1, q8) and cc1 == cc8  # deterministic chunked sum
+    e, ec = orc.eval_nodes(np.zeros((0, 6)))
+    assert e.shape == (0, 3) and ec == {"nf": 0, "naccept": 0, "nreject": 0, "nfail": 0}
+    # maxiters exhaustion is counted, not thrown (reference: failed retcode, g still applied)
+    short = oracle.OracleProblem.builtin("lotka_volterra", maxiters=5)
+    xs = sample_points("lotka_volterra", 10, seed=1)
+    d, c = short.eval_nodes(xs, weight_by_pdf=False)
+    assert c["nfail"] == 10 and c["naccept"] + c["nreject"] == 50 and np.all(np.isfinite(d))
