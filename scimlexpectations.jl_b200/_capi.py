@@ -391,11 +391,11 @@ class Handle:
         if len(shape) == 1:
             assert shape[0] % nx == 0
             return shape[0] // nx
-        if layout == LAYOUT_POINT_MAJOR:
-            assert shape[1] == nx, (shape, nx)
-            return shape[0]
-        assert shape[0] == nx, (shape, nx)
-        return shape[1]
+        if layout == LAYOUT_SOA:
+            assert shape[0] == nx, (shape, nx)
+            return shape[1]
+        assert shape[1] == nx, (shape, nx)   # point-major; an unknown layout code is rejected by the library
+        return shape[0]
 
     # -- the two hot entry points --
     def eval_nodes(self, x, *, layout=LAYOUT_POINT_MAJOR, weight_by_pdf=True, out=None, npts=None,

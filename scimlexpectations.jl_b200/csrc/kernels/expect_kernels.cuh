@@ -136,8 +136,17 @@ __device__ __forceinline__ void block_reduce_store(const b200e_kparams &P, Accum
 // ------------------------------------------------------------------------------------------
 // Adaptive Tsit5 (Tsitouras 2011) with OrdinaryDiffEq's defaults: Hairer-Wanner initial step,
 // PI controller beta1=7/50 beta2=2/25 gamma=9/10 qmin=1/5 qmax=10 qoldinit=1e-4, RMS error norm.
+//
+// FP64 instruction economy (ncu, profiles/r1_*): a 64-bit literal costs two UMOVs every time it is
+// used, and CUDA's log/exp/div/sqrt each carry a special-case branch.  So (1) every constant of
+// the step lives in __constant__ memory and is read as a c[bank][off] operand of the DFMA itself,
+// (2) the controller's power function is one branch-free log and one branch-free exp whose
+// coefficients sit in the same table, valid on the clamped domain the controller can reach, and
+// (3) the error scale uses MUFU.RCP64H + two Newton steps instead of an IEEE division.
 // ------------------------------------------------------------------------------------------
 #define R_(x) ((real)(x))
+
+namespace lit {
 constexpr double c1 = 0.161, c2 = 0.327, c3 = 0.9, c4 = 0.9800255409045097;
 constexpr double a21 = 0.161;
 constexpr double a31 = -0.008480655492356989, a32 = 0.335480655492357;
@@ -151,28 +160,110 @@ constexpr double a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996
 constexpr double bt1 = -0.00178001105222577714, bt2 = -0.0008164344596567469,
                  bt3 = 0.007880878010261995, bt4 = -0.1447110071732629, bt5 = 0.5823571654525552,
                  bt6 = -0.45808210592918697, bt7 = 0.015151515151515152;
+// PI controller on e2 = EEst^2:  EEst^b1 = e2^(b1/2)
+constexpr double hb1 = 0.5 * 7.0 / 50.0, hb2 = 0.5 * 2.0 / 25.0;
+constexpr double gamma = 9.0 / 10.0, qmin = 1.0 / 5.0, qmax = 10.0;
+constexpr double le2_qoldinit = -18.420680743952364;  // log(1e-4^2)
+constexpr double inv_n = 1.0 / B200E_NSTATE;
+// below / above these e2 the clamps decide alone (q = 1/qmax resp. reject factor = qmin):
+//   gamma * e2^-hb1 >= qmax  <=>  e2 <= (gamma/qmax)^(1/hb1) = 1.2e-15 ;  take 1e-30 for margin
+//   gamma * e2^-hb1 <= qmin  <=>  e2 >= (gamma/qmin)^(1/hb1) = 2.1e9   ;  take 1e12 for margin
+constexpr double e2_lo = 1e-30, e2_hi = 1e12;
+constexpr double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+constexpr double ln2 = 0.6931471805599453094, log2e = 1.4426950408889634074;
+constexpr double rnd_magic = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-nearest-integer
+constexpr double ln10_04 = 0.4 * 2.302585092994045684;
+}  // namespace lit
 
-constexpr double BETA1 = 7.0 / 50.0, BETA2 = 2.0 / 25.0, GAMMA = 9.0 / 10.0;
-constexpr double QMIN = 1.0 / 5.0, QMAX = 10.0;
-// log(qoldinit) = log(1e-4)
-constexpr double LOG_QOLDINIT = -9.210340371976182;
+#if B200E_FP32
+#define K_(name) ((real)lit::name)
+#else
+struct b200e_consts {
+    double c1, c2, c3, c4, a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, a71,
+        a72, a73, a74, a75, a76, bt1, bt2, bt3, bt4, bt5, bt6, bt7;
+    double hb1, hb2, gamma, qmin, qmax, le2_qoldinit, inv_n, e2_lo, e2_hi;
+    double ln2_hi, ln2_lo, ln2, log2e, rnd_magic, ln10_04;
+    double lg[10];  // atanh series 2/(2k+1), k = 0..9
+    double ex[13];  // 1/k!, k = 0..12
+};
+// not `const`: the compiler must read it from the constant bank instead of folding literals back in
+__constant__ b200e_consts KC = {
+    lit::c1, lit::c2, lit::c3, lit::c4, lit::a21, lit::a31, lit::a32, lit::a41, lit::a42, lit::a43, lit::a51,
+    lit::a52, lit::a53, lit::a54, lit::a61, lit::a62, lit::a63, lit::a64, lit::a65, lit::a71, lit::a72, lit::a73,
+    lit::a74, lit::a75, lit::a76, lit::bt1, lit::bt2, lit::bt3, lit::bt4, lit::bt5, lit::bt6, lit::bt7,
+    lit::hb1, lit::hb2, lit::gamma, lit::qmin, lit::qmax, lit::le2_qoldinit, lit::inv_n, lit::e2_lo, lit::e2_hi,
+    lit::ln2_hi, lit::ln2_lo, lit::ln2, lit::log2e, lit::rnd_magic, lit::ln10_04,
+    {2.0, 2.0 / 3, 2.0 / 5, 2.0 / 7, 2.0 / 9, 2.0 / 11, 2.0 / 13, 2.0 / 15, 2.0 / 17, 2.0 / 19},
+    {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+     1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600}};
+#define K_(name) (KC.name)
+#endif
+
+// ---- branch-free scalar helpers -----------------------------------------------------------
+#if B200E_FP32
+__device__ __forceinline__ float rcp_pos(float b) { return 1.0f / b; }
+__device__ __forceinline__ float log_pos(float x) { return logf(x); }
+__device__ __forceinline__ float exp_small(float y) { return expf(y); }
+__device__ __forceinline__ float sqrt_pos(float x) { return sqrtf(x); }
+#else
+// 1/b for normal b > 0: MUFU.RCP64H seed (~20 bits) + two Newton steps (20 -> 40 -> 80 bits)
+__device__ __forceinline__ double rcp_pos(double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    return fma(r, e, r);
+}
+// sqrt(x) for normal x > 0: MUFU.RSQ64H seed + two coupled Newton steps (Goldschmidt form)
+__device__ __forceinline__ double sqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, x);
+    return fma(d, h, g);
+}
+// log(x) for normal x > 0:  x = 2^e m, m in [sqrt(1/2), sqrt(2));  log m = 2 atanh((m-1)/(m+1))
+__device__ __forceinline__ double log_pos(double x) {
+    int hi = __double2hiint(x), lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    const int up = hi >= 0x3ff6a09f;  // m >= ~sqrt(2): halve it
+    hi -= up << 20;
+    e += up;
+    const double m = __hiloint2double(hi, lo);
+    const double s = (m - 1.0) * rcp_pos(m + 1.0);
+    const double z = s * s;
+    double p = K_(lg[9]);
+#pragma unroll
+    for (int k = 8; k >= 0; k--) p = fma(p, z, K_(lg[k]));
+    return fma((double)e, K_(ln2), s * p);
+}
+// exp(y) for |y| < 700 (no overflow / subnormal handling)
+__device__ __forceinline__ double exp_small(double y) {
+    const double t = fma(y, K_(log2e), K_(rnd_magic));
+    const int n = __double2loint(t);
+    const double nf = t - K_(rnd_magic);
+    double r = fma(-nf, K_(ln2_hi), y);
+    r = fma(-nf, K_(ln2_lo), r);
+    double p = K_(ex[12]);
+#pragma unroll
+    for (int k = 11; k >= 0; k--) p = fma(p, r, K_(ex[k]));
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+#endif
 
 enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
 
-// RMS norm of v[i]/sk[i] over the state (ODE_DEFAULT_NORM)
-__device__ __forceinline__ real rms_scaled(const real *v, const real *sk) {
-    real s = R_(0.0);
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        const real r = v[i] / sk[i];
-        s = fma(r, r, s);
-    }
-    return sqrt(s / R_(N));
-}
-
 // prob_func + integrator init for one lane: x -> (u0, p) via h, pdf weight, initial dt, FSAL k1
 __device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long long i, real *u, real *p,
-                                                 real *k1, real &t, real &dt, real &lqold, double &wgt,
+                                                 real *k1, real &t, real &dt, real &le2old, double &wgt,
                                                  unsigned &nf) {
     double xs[NX];
     load_point(P, i, xs);
@@ -188,13 +279,20 @@ __device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long lo
 
     t = (real)P.t0;
     const real abstol = (real)P.abstol, reltol = (real)P.reltol, dtmax = (real)P.dtmax;
-    real f0[N], sk[N];
+    // Hairer-Wanner initial step (ode_determine_initdt) on squared norms: one sqrt, one log, one exp
+    real f0[N], isk[N];
     rhs(f0, u, p, t);
+    real s0 = R_(0.0), s1 = R_(0.0);
 #pragma unroll
-    for (int j = 0; j < N; j++) sk[j] = fma(fabs(u[j]), reltol, abstol);
-    const real d0 = rms_scaled(u, sk);
-    const real d1 = rms_scaled(f0, sk);
-    real dt0 = (d0 < R_(1e-5) || d1 < R_(1e-5)) ? R_(1e-6) : (d0 / d1) / R_(100.0);
+    for (int j = 0; j < N; j++) {
+        isk[j] = rcp_pos(fma(fabs(u[j]), reltol, abstol));
+        const real a = u[j] * isk[j], b = f0[j] * isk[j];
+        s0 = fma(a, a, s0);
+        s1 = fma(b, b, s1);
+    }
+    // d0 = sqrt(s0/N), d1 = sqrt(s1/N):  d0 < 1e-5  <=>  s0 < N * 1e-10
+    const real tiny2 = R_(1e-10) * R_(N);
+    real dt0 = (s0 < tiny2 || s1 < tiny2) ? R_(1e-6) : R_(0.01) * sqrt_pos(s0 * rcp_pos(s1));
     dt0 = fmin(dt0, dtmax);
 #if B200E_FP32
     const real eps10 = R_(10.0) * R_(1.1920928955078125e-07);
@@ -205,17 +303,22 @@ __device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long lo
         dt = R_(1e-6);
         nf += 2u;
     } else {
-        real u1[N], f1[N], df[N];
+        real u1[N], f1[N];
 #pragma unroll
         for (int j = 0; j < N; j++) u1[j] = fma(dt0, f0[j], u[j]);
         rhs(f1, u1, p, t + dt0);
+        real s2 = R_(0.0);
 #pragma unroll
-        for (int j = 0; j < N; j++) df[j] = f1[j] - f0[j];
-        const real d2 = rms_scaled(df, sk) / dt0;
-        const real dmax = fmax(d1, d2);
+        for (int j = 0; j < N; j++) {
+            const real d = (f1[j] - f0[j]) * isk[j];
+            s2 = fma(d, d, s2);
+        }
+        // dmax^2 = max(d1^2, d2^2) with d2 = sqrt(s2/N)/dt0
+        const real idt0 = rcp_pos(dt0);
+        const real m2 = fmax(s1, s2 * idt0 * idt0) * R_(lit::inv_n);
         real dt1;
-        if (dmax <= R_(1e-15)) dt1 = fmax(R_(1e-6), dt0 * R_(1e-3));
-        else dt1 = exp10(-(R_(2.0) + log10(dmax)) / R_(5.0));
+        if (m2 <= R_(1e-30)) dt1 = fmax(R_(1e-6), dt0 * R_(1e-3));
+        else dt1 = exp_small(fma(R_(-0.1), log_pos(m2), -K_(ln10_04)));  // 10^(-(2 + log10 dmax)/5)
         dt = fmin(fmin(R_(100.0) * dt0, dt1), dtmax);
         nf += 3u;
     }
@@ -223,7 +326,7 @@ __device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long lo
     // again, so it is counted again)
 #pragma unroll
     for (int j = 0; j < N; j++) k1[j] = f0[j];
-    lqold = R_(LOG_QOLDINIT);
+    le2old = K_(le2_qoldinit);
 }
 
 template <bool REDUCE>
@@ -233,11 +336,11 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     long long cur = -1;
 
     real u[N], k1[N], p[B200E_DIM(NP)];
-    real t = R_(0.0), dt = R_(0.0), lqold = R_(0.0);
+    real t = R_(0.0), dt = R_(0.0), le2old = R_(0.0);
     double wgt = 1.0;
     int state = LANE_EMPTY;
     int failed = 0;
-    long long iter = 0;
+    int iter = 0;
     unsigned tnf = 0, tacc = 0, trej = 0;  // counters of the current trajectory
     Accum A;
     A.zero();
@@ -245,6 +348,7 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     const real t1 = (real)P.t1, dtmax = (real)P.dtmax;
     const real abstol = (real)P.abstol, reltol = (real)P.reltol;
     const real snap_tol = (real)P.snap_tol;
+    const int maxiters = (int)P.maxiters;
 #if B200E_FP32
     const real one_plus_eps = R_(1.0) + R_(1.1920928955078125e-07);
 #else
@@ -270,18 +374,17 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                     cur = next;
                     next += T;
                     tnf = 0; tacc = 0; trej = 0; failed = 0; iter = 0;
-                    start_trajectory(P, cur, u, p, k1, t, dt, lqold, wgt, tnf);
+                    start_trajectory(P, cur, u, p, k1, t, dt, le2old, wgt, tnf);
                     state = (t < t1) ? LANE_ACTIVE : LANE_DONE;
                 }
             }
         }
         if (state == LANE_ACTIVE) {
-            // ---- loopheader!: iteration cap, dt bounds, clip to the end point ----
+            // ---- loopheader!: iteration cap, clip to the end point (dt <= dtmax holds already:
+            // it is enforced where dt is proposed; fmin drops a NaN, so dt is finite here) ----
             iter++;
-            dt = fmin(dt, dtmax);
             dt = fmin(dt, t1 - t);
-            const bool bad_dt = !(fabs(dt) <= R_(1.79e308)) || (t + dt == t);  // NaN/Inf/underflow
-            if (iter > P.maxiters || bad_dt) {
+            if (iter > maxiters || t + dt == t) {  // maxiters / dt below the resolution of t
                 failed = 1;
                 state = LANE_DONE;
                 continue;
@@ -289,67 +392,68 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
             // ---- perform_step!: 6 new stages, FSAL ----
             real k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], tmp[N], un[N];
 #pragma unroll
-            for (int i = 0; i < N; i++) tmp[i] = fma(dt, R_(a21) * k1[i], u[i]);
-            rhs(k2, tmp, p, fma(R_(c1), dt, t));
+            for (int i = 0; i < N; i++) tmp[i] = fma(dt, K_(a21) * k1[i], u[i]);
+            rhs(k2, tmp, p, fma(K_(c1), dt, t));
 #pragma unroll
-            for (int i = 0; i < N; i++) tmp[i] = fma(dt, fma(R_(a32), k2[i], R_(a31) * k1[i]), u[i]);
-            rhs(k3, tmp, p, fma(R_(c2), dt, t));
-#pragma unroll
-            for (int i = 0; i < N; i++)
-                tmp[i] = fma(dt, fma(R_(a43), k3[i], fma(R_(a42), k2[i], R_(a41) * k1[i])), u[i]);
-            rhs(k4, tmp, p, fma(R_(c3), dt, t));
+            for (int i = 0; i < N; i++) tmp[i] = fma(dt, fma(K_(a32), k2[i], K_(a31) * k1[i]), u[i]);
+            rhs(k3, tmp, p, fma(K_(c2), dt, t));
 #pragma unroll
             for (int i = 0; i < N; i++)
-                tmp[i] = fma(dt, fma(R_(a54), k4[i], fma(R_(a53), k3[i], fma(R_(a52), k2[i], R_(a51) * k1[i]))),
+                tmp[i] = fma(dt, fma(K_(a43), k3[i], fma(K_(a42), k2[i], K_(a41) * k1[i])), u[i]);
+            rhs(k4, tmp, p, fma(K_(c3), dt, t));
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                tmp[i] = fma(dt, fma(K_(a54), k4[i], fma(K_(a53), k3[i], fma(K_(a52), k2[i], K_(a51) * k1[i]))),
                              u[i]);
-            rhs(k5, tmp, p, fma(R_(c4), dt, t));
+            rhs(k5, tmp, p, fma(K_(c4), dt, t));
 #pragma unroll
             for (int i = 0; i < N; i++)
                 tmp[i] = fma(dt,
-                             fma(R_(a65), k5[i],
-                                 fma(R_(a64), k4[i], fma(R_(a63), k3[i], fma(R_(a62), k2[i], R_(a61) * k1[i])))),
+                             fma(K_(a65), k5[i],
+                                 fma(K_(a64), k4[i], fma(K_(a63), k3[i], fma(K_(a62), k2[i], K_(a61) * k1[i])))),
                              u[i]);
             rhs(k6, tmp, p, t + dt);
 #pragma unroll
             for (int i = 0; i < N; i++)
                 un[i] = fma(dt,
-                            fma(R_(a76), k6[i],
-                                fma(R_(a75), k5[i],
-                                    fma(R_(a74), k4[i], fma(R_(a73), k3[i], fma(R_(a72), k2[i], R_(a71) * k1[i]))))),
+                            fma(K_(a76), k6[i],
+                                fma(K_(a75), k5[i],
+                                    fma(K_(a74), k4[i], fma(K_(a73), k3[i], fma(K_(a72), k2[i], K_(a71) * k1[i]))))),
                             u[i]);
             rhs(k7, un, p, t + dt);
             tnf += 6u;
 
-            // ---- embedded error estimate: calculate_residuals + RMS norm ----
+            // ---- embedded error estimate: calculate_residuals + RMS norm, kept squared ----
             real ss = R_(0.0);
 #pragma unroll
             for (int i = 0; i < N; i++) {
                 const real ut =
-                    dt * fma(R_(bt7), k7[i],
-                             fma(R_(bt6), k6[i],
-                                 fma(R_(bt5), k5[i],
-                                     fma(R_(bt4), k4[i], fma(R_(bt3), k3[i], fma(R_(bt2), k2[i], R_(bt1) * k1[i]))))));
+                    dt * fma(K_(bt7), k7[i],
+                             fma(K_(bt6), k6[i],
+                                 fma(K_(bt5), k5[i],
+                                     fma(K_(bt4), k4[i], fma(K_(bt3), k3[i], fma(K_(bt2), k2[i], K_(bt1) * k1[i]))))));
                 const real sc = fma(fmax(fabs(u[i]), fabs(un[i])), reltol, abstol);
-                const real r = ut / sc;
+                const real r = ut * rcp_pos(sc);
                 ss = fma(r, r, ss);
             }
-            const real e2 = ss * (R_(1.0) / R_(N));  // EEst^2
+            const real e2 = ss * K_(inv_n);  // EEst^2
             if (!(e2 == e2)) {  // NaN estimate: the reference rejects, dt turns NaN, solve aborts
                 trej++;
                 failed = 1;
                 state = LANE_DONE;
                 continue;
             }
-            // ---- PI controller in log space: one log + one exp instead of two pow + sqrt ----
-            // q = EEst^b1 / qold^b2 / gamma clamped to [1/qmax, 1/qmin]; we form 1/q directly.
-            const real le = (e2 > R_(0.0)) ? R_(0.5) * log(e2) : neg_inf();  // log(EEst)
+            // ---- PI controller in log space on e2: one log + one exp instead of two pow + sqrt ----
+            // q = EEst^b1 / qold^b2 / gamma clamped to [1/qmax, 1/qmin]; 1/q is formed directly.
+            const bool mid = (e2 > K_(e2_lo)) && (e2 < K_(e2_hi));
+            const real le2 = mid ? log_pos(e2) : K_(le2_qoldinit);
             if (e2 <= one_plus_eps) {  // sqrt(e2) <= 1  <=>  e2 <= nextafter(1)
-                real qinv = R_(QMAX);
-                if (e2 > R_(0.0)) {
-                    qinv = R_(GAMMA) * exp(fma(R_(BETA2), lqold, -R_(BETA1) * le));
-                    qinv = fmin(R_(QMAX), fmax(R_(QMIN), qinv));
+                real qinv = K_(qmax);  // e2 <= e2_lo: the 1/qmax clamp decides alone
+                if (mid) {
+                    qinv = K_(gamma) * exp_small(fma(K_(hb2), le2old, -K_(hb1) * le2));
+                    qinv = fmin(K_(qmax), fmax(K_(qmin), qinv));
                 }
-                lqold = fmax(le, R_(LOG_QOLDINIT));
+                le2old = fmax(le2, K_(le2_qoldinit));  // qold = max(EEst, 1e-4)
                 real tn = t + dt;
                 if (fabs(tn - t1) < snap_tol) tn = t1;  // fixed_t_for_floatingpoint_error!
                 t = tn;
@@ -359,8 +463,9 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 tacc++;
                 if (!(t < t1)) state = LANE_DONE;
             } else {
-                // step_reject_controller!: dt /= min(1/qmin, q11/gamma)
-                const real f = fmax(R_(QMIN), R_(GAMMA) * exp(-R_(BETA1) * le));
+                // step_reject_controller!: dt /= min(1/qmin, q11/gamma);  e2 >= e2_hi: qmin decides
+                real f = K_(qmin);
+                if (mid) f = fmax(K_(qmin), K_(gamma) * exp_small(-K_(hb1) * le2));
                 dt = dt * f;
                 trej++;
             }
