@@ -58,15 +58,28 @@ __device__ __forceinline__ void load_point(const b200e_kparams &P, long long i, 
     }
 }
 
-// per-lane running sums of the batch; flushed once per launch
+// Per-lane running sums of the batch, flushed once per launch.  They are touched once per
+// TRAJECTORY (not per step), so they live in shared memory, one conflict-free column per thread,
+// and stay out of the register budget of the step loop (registers decide how many warps are
+// resident, and resident warps are what hides the FP64 dependency chains).
+constexpr bool ACC_SMEM = (NACC * 8 + 4 * 8) * B200E_BLOCK <= 16384;
+__shared__ double sh_acc[ACC_SMEM ? NACC : 1][B200E_BLOCK];
+__shared__ unsigned long long sh_cnt[ACC_SMEM ? 4 : 1][B200E_BLOCK];
+
 struct Accum {
-    double s[NOUT];
-    double s2[NOUT];
-    unsigned long long nf, nacc, nrej, nfail;
-    __device__ __forceinline__ void zero() {
+    // register fallback for wide observables (NACC columns of shared memory would not fit)
+    double rs[ACC_SMEM ? 1 : NACC];
+    unsigned long long rc[ACC_SMEM ? 1 : 4];
+    __device__ __forceinline__ double &val(int k) { return ACC_SMEM ? sh_acc[ACC_SMEM ? k : 0][threadIdx.x] : rs[ACC_SMEM ? 0 : k]; }
+    __device__ __forceinline__ unsigned long long &cnt(int j) { return ACC_SMEM ? sh_cnt[ACC_SMEM ? j : 0][threadIdx.x] : rc[ACC_SMEM ? 0 : j]; }
+    __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int k = 0; k < NOUT; k++) { s[k] = 0.0; s2[k] = 0.0; }
-        nf = nacc = nrej = nfail = 0ull;
+        for (int k = 0; k < NACC; k++) val(k) = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) cnt(j) = 0ull;
+    }
+    __device__ __forceinline__ void count(unsigned nf, unsigned nacc, unsigned nrej, unsigned nfail) {
+        cnt(0) += nf; cnt(1) += nacc; cnt(2) += nrej; cnt(3) += nfail;
     }
 };
 
@@ -81,8 +94,8 @@ __device__ __forceinline__ void emit(const b200e_kparams &P, long long i, const 
         double v = (double)out[k];
         if (P.weight_by_pdf) v *= wgt;
         if (REDUCE) {
-            A.s[k] += v;
-            A.s2[k] = fma(v, v, A.s2[k]);
+            A.val(k) += v;
+            A.val(NOUT + k) = fma(v, v, A.val(NOUT + k));
         } else {
             if (P.layout == 0) P.dx[i * NOUT + k] = v;
             else P.dx[(long long)k * P.ld + i] = v;
@@ -97,15 +110,17 @@ __device__ __forceinline__ void block_reduce_store(const b200e_kparams &P, Accum
     __shared__ double sacc[NWARPS][NACC];
     __shared__ unsigned long long scnt[NWARPS][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long cnt[4] = {A.nf, A.nacc, A.nrej, A.nfail};
+    unsigned long long cnt[4];
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < 4; k++) cnt[k] = A.cnt(k);
+#pragma unroll
+    for (int k = 0; k < NACC; k++) acc[k] = A.val(k);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         if (REDUCE) {
 #pragma unroll
-            for (int k = 0; k < NOUT; k++) {
-                A.s[k] += __shfl_down_sync(B200E_FULL, A.s[k], off);
-                A.s2[k] += __shfl_down_sync(B200E_FULL, A.s2[k], off);
-            }
+            for (int k = 0; k < NACC; k++) acc[k] += __shfl_down_sync(B200E_FULL, acc[k], off);
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) cnt[k] += __shfl_down_sync(B200E_FULL, cnt[k], off);
@@ -113,7 +128,7 @@ __device__ __forceinline__ void block_reduce_store(const b200e_kparams &P, Accum
     if (lane == 0) {
         if (REDUCE) {
 #pragma unroll
-            for (int k = 0; k < NOUT; k++) { sacc[warp][k] = A.s[k]; sacc[warp][NOUT + k] = A.s2[k]; }
+            for (int k = 0; k < NACC; k++) sacc[warp][k] = acc[k];
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) scnt[warp][k] = cnt[k];
@@ -240,9 +255,13 @@ __device__ __forceinline__ double log_pos(double x) {
     const double m = __hiloint2double(hi, lo);
     const double s = (m - 1.0) * rcp_pos(m + 1.0);
     const double z = s * s;
-    double p = K_(lg[9]);
-#pragma unroll
-    for (int k = 8; k >= 0; k--) p = fma(p, z, K_(lg[k]));
+    // Estrin: depth 5 instead of 10 dependent DFMAs (4 resident warps cannot hide a long chain)
+    const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+    const double q01 = fma(K_(lg[1]), z, K_(lg[0])), q23 = fma(K_(lg[3]), z, K_(lg[2]));
+    const double q45 = fma(K_(lg[5]), z, K_(lg[4])), q67 = fma(K_(lg[7]), z, K_(lg[6]));
+    const double q89 = fma(K_(lg[9]), z, K_(lg[8]));
+    const double q03 = fma(q23, z2, q01), q47 = fma(q67, z2, q45);
+    const double p = fma(q89, z8, fma(q47, z4, q03));
     return fma((double)e, K_(ln2), s * p);
 }
 // exp(y) for |y| < 700 (no overflow / subnormal handling)
@@ -252,9 +271,13 @@ __device__ __forceinline__ double exp_small(double y) {
     const double nf = t - K_(rnd_magic);
     double r = fma(-nf, K_(ln2_hi), y);
     r = fma(-nf, K_(ln2_lo), r);
-    double p = K_(ex[12]);
-#pragma unroll
-    for (int k = 11; k >= 0; k--) p = fma(p, r, K_(ex[k]));
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double q01 = fma(K_(ex[1]), r, K_(ex[0])), q23 = fma(K_(ex[3]), r, K_(ex[2]));
+    const double q45 = fma(K_(ex[5]), r, K_(ex[4])), q67 = fma(K_(ex[7]), r, K_(ex[6]));
+    const double q89 = fma(K_(ex[9]), r, K_(ex[8])), qab = fma(K_(ex[11]), r, K_(ex[10]));
+    const double q03 = fma(q23, r2, q01), q47 = fma(q67, r2, q45);
+    const double q8c = fma(K_(ex[12]), r4, fma(qab, r2, q89));
+    const double p = fma(q8c, r8, fma(q47, r4, q03));
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 #endif
@@ -329,21 +352,131 @@ __device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long lo
     le2old = K_(le2_qoldinit);
 }
 
+// min / max of two NON-NEGATIVE reals through their bit patterns (IEEE order == integer order
+// for x >= 0): integer-pipe compares + selects instead of a DSETP on the FP64 pipe plus the
+// NaN-fixup sequence fmin/fmax compile to.  A positive-NaN pattern orders above +inf.
+#if B200E_FP32
+__device__ __forceinline__ float pmin(float a, float b) { return __int_as_float(min(__float_as_int(a), __float_as_int(b))); }
+__device__ __forceinline__ float pmax(float a, float b) { return __int_as_float(max(__float_as_int(a), __float_as_int(b))); }
+#else
+__device__ __forceinline__ double pmin(double a, double b) {
+    return __longlong_as_double(min(__double_as_longlong(a), __double_as_longlong(b)));
+}
+__device__ __forceinline__ double pmax(double a, double b) {
+    return __longlong_as_double(max(__double_as_longlong(a), __double_as_longlong(b)));
+}
+#endif
+
+// One attempted Tsit5 step of the lane's trajectory (perform_step! + stepsize_controller! +
+// step_accept/reject_controller! + the loopheader! checks of the reference's integrator loop).
+struct Lane {
+    real u[N], k1[N], p[B200E_DIM(NP)];
+    real t, dt, le2old;
+    int state;
+    int failed;  // 0 ok, 1 aborted, 2 NaN error estimate seen: abort at the next loop header
+    unsigned nf0, nacc, nrej;  // nf = nf0 (initial-step evaluations) + 6 * (nacc + nrej)
+};
+
+__device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dtmax, const real abstol,
+                                           const real reltol, const real snap_tol, const int maxiters,
+                                           const real one_plus_eps) {
+    real *u = L.u, *k1 = L.k1, *p = L.p;
+    const real t = L.t;
+    // ---- loopheader!: a NaN error estimate in the previous attempt, the iteration cap, or a step
+    // below the resolution of t abort the trajectory (dt <= dtmax holds where dt is proposed) ----
+    const real dt = pmin(L.dt, t1 - t);  // clip to the end point
+    if (L.failed || (int)(L.nacc + L.nrej) >= maxiters || t + dt == t) {
+        L.failed = 1;
+        L.state = LANE_DONE;
+        return;
+    }
+    // ---- perform_step!: 6 new stages, FSAL ----
+    real k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], tmp[N], un[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) tmp[i] = fma(dt, K_(a21) * k1[i], u[i]);
+    rhs(k2, tmp, p, fma(K_(c1), dt, t));
+#pragma unroll
+    for (int i = 0; i < N; i++) tmp[i] = fma(dt, fma(K_(a32), k2[i], K_(a31) * k1[i]), u[i]);
+    rhs(k3, tmp, p, fma(K_(c2), dt, t));
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        tmp[i] = fma(dt, fma(K_(a43), k3[i], fma(K_(a42), k2[i], K_(a41) * k1[i])), u[i]);
+    rhs(k4, tmp, p, fma(K_(c3), dt, t));
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        tmp[i] = fma(dt, fma(K_(a54), k4[i], fma(K_(a53), k3[i], fma(K_(a52), k2[i], K_(a51) * k1[i]))), u[i]);
+    rhs(k5, tmp, p, fma(K_(c4), dt, t));
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        tmp[i] = fma(dt,
+                     fma(K_(a65), k5[i],
+                         fma(K_(a64), k4[i], fma(K_(a63), k3[i], fma(K_(a62), k2[i], K_(a61) * k1[i])))),
+                     u[i]);
+    rhs(k6, tmp, p, t + dt);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        un[i] = fma(dt,
+                    fma(K_(a76), k6[i],
+                        fma(K_(a75), k5[i],
+                            fma(K_(a74), k4[i], fma(K_(a73), k3[i], fma(K_(a72), k2[i], K_(a71) * k1[i]))))),
+                    u[i]);
+    rhs(k7, un, p, t + dt);
+
+    // ---- embedded error estimate: calculate_residuals + RMS norm, kept squared ----
+    real ss = R_(0.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const real ut =
+            dt * fma(K_(bt7), k7[i],
+                     fma(K_(bt6), k6[i],
+                         fma(K_(bt5), k5[i],
+                             fma(K_(bt4), k4[i], fma(K_(bt3), k3[i], fma(K_(bt2), k2[i], K_(bt1) * k1[i]))))));
+        const real sc = fma(pmax(fabs(u[i]), fabs(un[i])), reltol, abstol);
+        const real r = ut * rcp_pos(sc);
+        ss = fma(r, r, ss);
+    }
+    const real e2 = ss * K_(inv_n);  // EEst^2
+    // NaN estimate: the reference counts a rejection, dt turns NaN and the solve aborts at the next
+    // loop header -- same here through L.failed = 2 (the accept test below is false for a NaN)
+    L.failed = (e2 == e2) ? 0 : 2;
+    const bool accept = e2 <= one_plus_eps;  // sqrt(e2) <= 1  <=>  e2 <= nextafter(1)
+
+    // ---- PI controller in log space on e2: one log + one exp instead of two pow + sqrt ----
+    // accept:  1/q = gamma * qold^b2 / EEst^b1  clamped to [qmin, qmax]
+    // reject:  dt *= max(qmin, gamma / EEst^b1)  (< 1, so the same clamp applies)
+    // Outside [e2_lo, e2_hi] the clamps decide alone, so e2 is clamped first and the log never
+    // sees 0, inf or a subnormal.
+    const real le2 = log_pos(pmin(pmax(e2, K_(e2_lo)), K_(e2_hi)));
+    const real hist = accept ? L.le2old : R_(0.0);
+    real qinv = K_(gamma) * exp_small(fma(K_(hb2), hist, -K_(hb1) * le2));
+    qinv = pmin(K_(qmax), pmax(K_(qmin), qinv));
+    L.dt = pmin(dtmax, dt * qinv);
+    if (accept) {
+        L.le2old = fmax(le2, K_(le2_qoldinit));  // qold = max(EEst, 1e-4)
+        real tn = t + dt;
+        if (fabs(tn - t1) < snap_tol) tn = t1;  // fixed_t_for_floatingpoint_error!
+        L.t = tn;
+#pragma unroll
+        for (int i = 0; i < N; i++) { u[i] = un[i]; k1[i] = k7[i]; }
+        L.nacc++;
+        if (!(tn < t1)) L.state = LANE_DONE;
+    } else {
+        L.nrej++;
+    }
+}
+
 template <bool REDUCE>
 __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
-    const long long T = (long long)gridDim.x * B200E_BLOCK;
     long long next = (long long)blockIdx.x * B200E_BLOCK + threadIdx.x;
     long long cur = -1;
 
-    real u[N], k1[N], p[B200E_DIM(NP)];
-    real t = R_(0.0), dt = R_(0.0), le2old = R_(0.0);
+    Lane L;
+    L.t = R_(0.0); L.dt = R_(0.0); L.le2old = R_(0.0);
+    L.state = LANE_EMPTY; L.failed = 0;
+    L.nf0 = 0; L.nacc = 0; L.nrej = 0;
     double wgt = 1.0;
-    int state = LANE_EMPTY;
-    int failed = 0;
-    int iter = 0;
-    unsigned tnf = 0, tacc = 0, trej = 0;  // counters of the current trajectory
     Accum A;
-    A.zero();
+    A.init();
 
     const real t1 = (real)P.t1, dtmax = (real)P.dtmax;
     const real abstol = (real)P.abstol, reltol = (real)P.reltol;
@@ -356,120 +489,36 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
 #endif
 
     for (;;) {
-        const bool wants = (state == LANE_DONE) || (state == LANE_EMPTY && next < P.npts);
+        // ---- refill phase: runs only when the set of stepping lanes has changed ----
+        const bool wants = (L.state == LANE_DONE) || (L.state == LANE_EMPTY && next < P.npts);
         const unsigned idle_m = __ballot_sync(B200E_FULL, wants);
-        const unsigned act_m = __ballot_sync(B200E_FULL, state == LANE_ACTIVE);
+        unsigned act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
         if ((idle_m | act_m) == 0u) break;
         const int live = __popc(idle_m | act_m);
         const int thr = P.refill_threshold < live ? P.refill_threshold : live;
         if (__popc(idle_m) >= thr) {  // warp-uniform
             if (wants) {
-                if (state == LANE_DONE) {
-                    emit<REDUCE>(P, cur, u, p, wgt, A);
-                    if (!REDUCE && P.steps) P.steps[cur] = (int)(tacc + trej);
-                    A.nf += tnf; A.nacc += tacc; A.nrej += trej; A.nfail += (unsigned)failed;
-                    state = LANE_EMPTY;
+                if (L.state == LANE_DONE) {
+                    emit<REDUCE>(P, cur, L.u, L.p, wgt, A);
+                    if (!REDUCE && P.steps) P.steps[cur] = (int)(L.nacc + L.nrej);
+                    A.count(L.nf0 + 6u * (L.nacc + L.nrej), L.nacc, L.nrej, L.failed ? 1u : 0u);
+                    L.state = LANE_EMPTY;
                 }
                 if (next < P.npts) {
                     cur = next;
-                    next += T;
-                    tnf = 0; tacc = 0; trej = 0; failed = 0; iter = 0;
-                    start_trajectory(P, cur, u, p, k1, t, dt, le2old, wgt, tnf);
-                    state = (t < t1) ? LANE_ACTIVE : LANE_DONE;
+                    next += (long long)gridDim.x * B200E_BLOCK;
+                    L.nf0 = 0; L.nacc = 0; L.nrej = 0; L.failed = 0;
+                    start_trajectory(P, cur, L.u, L.p, L.k1, L.t, L.dt, L.le2old, wgt, L.nf0);
+                    L.state = (L.t < t1) ? LANE_ACTIVE : LANE_DONE;
                 }
             }
+            act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
         }
-        if (state == LANE_ACTIVE) {
-            // ---- loopheader!: iteration cap, clip to the end point (dt <= dtmax holds already:
-            // it is enforced where dt is proposed; fmin drops a NaN, so dt is finite here) ----
-            iter++;
-            dt = fmin(dt, t1 - t);
-            if (iter > maxiters || t + dt == t) {  // maxiters / dt below the resolution of t
-                failed = 1;
-                state = LANE_DONE;
-                continue;
-            }
-            // ---- perform_step!: 6 new stages, FSAL ----
-            real k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], tmp[N], un[N];
-#pragma unroll
-            for (int i = 0; i < N; i++) tmp[i] = fma(dt, K_(a21) * k1[i], u[i]);
-            rhs(k2, tmp, p, fma(K_(c1), dt, t));
-#pragma unroll
-            for (int i = 0; i < N; i++) tmp[i] = fma(dt, fma(K_(a32), k2[i], K_(a31) * k1[i]), u[i]);
-            rhs(k3, tmp, p, fma(K_(c2), dt, t));
-#pragma unroll
-            for (int i = 0; i < N; i++)
-                tmp[i] = fma(dt, fma(K_(a43), k3[i], fma(K_(a42), k2[i], K_(a41) * k1[i])), u[i]);
-            rhs(k4, tmp, p, fma(K_(c3), dt, t));
-#pragma unroll
-            for (int i = 0; i < N; i++)
-                tmp[i] = fma(dt, fma(K_(a54), k4[i], fma(K_(a53), k3[i], fma(K_(a52), k2[i], K_(a51) * k1[i]))),
-                             u[i]);
-            rhs(k5, tmp, p, fma(K_(c4), dt, t));
-#pragma unroll
-            for (int i = 0; i < N; i++)
-                tmp[i] = fma(dt,
-                             fma(K_(a65), k5[i],
-                                 fma(K_(a64), k4[i], fma(K_(a63), k3[i], fma(K_(a62), k2[i], K_(a61) * k1[i])))),
-                             u[i]);
-            rhs(k6, tmp, p, t + dt);
-#pragma unroll
-            for (int i = 0; i < N; i++)
-                un[i] = fma(dt,
-                            fma(K_(a76), k6[i],
-                                fma(K_(a75), k5[i],
-                                    fma(K_(a74), k4[i], fma(K_(a73), k3[i], fma(K_(a72), k2[i], K_(a71) * k1[i]))))),
-                            u[i]);
-            rhs(k7, un, p, t + dt);
-            tnf += 6u;
-
-            // ---- embedded error estimate: calculate_residuals + RMS norm, kept squared ----
-            real ss = R_(0.0);
-#pragma unroll
-            for (int i = 0; i < N; i++) {
-                const real ut =
-                    dt * fma(K_(bt7), k7[i],
-                             fma(K_(bt6), k6[i],
-                                 fma(K_(bt5), k5[i],
-                                     fma(K_(bt4), k4[i], fma(K_(bt3), k3[i], fma(K_(bt2), k2[i], K_(bt1) * k1[i]))))));
-                const real sc = fma(fmax(fabs(u[i]), fabs(un[i])), reltol, abstol);
-                const real r = ut * rcp_pos(sc);
-                ss = fma(r, r, ss);
-            }
-            const real e2 = ss * K_(inv_n);  // EEst^2
-            if (!(e2 == e2)) {  // NaN estimate: the reference rejects, dt turns NaN, solve aborts
-                trej++;
-                failed = 1;
-                state = LANE_DONE;
-                continue;
-            }
-            // ---- PI controller in log space on e2: one log + one exp instead of two pow + sqrt ----
-            // q = EEst^b1 / qold^b2 / gamma clamped to [1/qmax, 1/qmin]; 1/q is formed directly.
-            const bool mid = (e2 > K_(e2_lo)) && (e2 < K_(e2_hi));
-            const real le2 = mid ? log_pos(e2) : K_(le2_qoldinit);
-            if (e2 <= one_plus_eps) {  // sqrt(e2) <= 1  <=>  e2 <= nextafter(1)
-                real qinv = K_(qmax);  // e2 <= e2_lo: the 1/qmax clamp decides alone
-                if (mid) {
-                    qinv = K_(gamma) * exp_small(fma(K_(hb2), le2old, -K_(hb1) * le2));
-                    qinv = fmin(K_(qmax), fmax(K_(qmin), qinv));
-                }
-                le2old = fmax(le2, K_(le2_qoldinit));  // qold = max(EEst, 1e-4)
-                real tn = t + dt;
-                if (fabs(tn - t1) < snap_tol) tn = t1;  // fixed_t_for_floatingpoint_error!
-                t = tn;
-#pragma unroll
-                for (int i = 0; i < N; i++) { u[i] = un[i]; k1[i] = k7[i]; }
-                dt = fmin(dtmax, dt * qinv);
-                tacc++;
-                if (!(t < t1)) state = LANE_DONE;
-            } else {
-                // step_reject_controller!: dt /= min(1/qmin, q11/gamma);  e2 >= e2_hi: qmin decides
-                real f = K_(qmin);
-                if (mid) f = fmax(K_(qmin), K_(gamma) * exp_small(-K_(hb1) * le2));
-                dt = dt * f;
-                trej++;
-            }
-        }
+        if (act_m == 0u) continue;
+        // ---- step phase: a tight loop, one vote per step, until some lane finishes ----
+        do {
+            if (L.state == LANE_ACTIVE) tsit5_step(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps);
+        } while (__ballot_sync(B200E_FULL, L.state == LANE_ACTIVE) == act_m);
     }
     block_reduce_store<REDUCE>(P, A);
 }
@@ -496,7 +545,7 @@ template <bool REDUCE>
 __device__ __forceinline__ void em_run(const b200e_kparams &P) {
     const long long T = (long long)gridDim.x * B200E_BLOCK;
     Accum A;
-    A.zero();
+    A.init();
     const long long nsteps = P.em_nsteps;
     const real t0 = (real)P.t0, t1 = (real)P.t1, h = (real)P.dt_fixed;
     for (long long i = (long long)blockIdx.x * B200E_BLOCK + threadIdx.x; i < P.npts; i += T) {
@@ -540,9 +589,7 @@ __device__ __forceinline__ void em_run(const b200e_kparams &P) {
         for (int j = 0; j < N; j++) failed |= !(u[j] == u[j]);
         emit<REDUCE>(P, i, u, p, wgt, A);
         if (!REDUCE && P.steps) P.steps[i] = (int)nsteps;
-        A.nf += (unsigned long long)nsteps;
-        A.nacc += (unsigned long long)nsteps;
-        A.nfail += (unsigned)failed;
+        A.count((unsigned)nsteps, (unsigned)nsteps, 0u, (unsigned)failed);
     }
     block_reduce_store<REDUCE>(P, A);
 }
