@@ -1,0 +1,136 @@
+# B200Expectations.jl -- thin ccall shim that plugs libb200expect.so into SciMLExpectations.jl.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  It is a literal mirror of the
+# ctypes calls in scimlexpectations.jl_b200/_capi.py (which ARE tested, on a B200, through the same C
+# ABI), kept short so a maintainer can check it against include/b200_expect.h line by line.
+#
+# What it does: defines `EnsembleB200 <: SciMLBase.EnsembleAlgorithm` for the `ensemblealg` slot of
+# `SystemMap(prob, alg, ensemblealg; kwargs...)` (reference src/system_utils.jl:48-53) and specialises the
+# two methods that consume that slot,
+#     build_integrand(::ExpectationProblem{<:SystemMap{..,EnsembleB200}}, ::Koopman, mid, p, batch::Integer)
+#                                                        (reference src/expectation.jl:169-200)
+#     solve(::ExpectationProblem{<:SystemMap{..,EnsembleB200}}, ::MonteCarlo)
+#                                                        (reference src/expectation.jl:268-294)
+# so that `solve(exprob, Koopman(); batch=..., quadalg=CubatureJLh())` and `solve(exprob, MonteCarlo(n))`
+# keep their signatures.  Julia closures cannot run on the device: f, g, h travel as CUDA source
+# (fields of `B200Model`); `h`/`g` of the structured forms (scatter x into u0/p, end-state components)
+# can be generated with `hmap_scatter` / `observable_components` below.
+module B200Expectations
+
+using SciMLExpectations, SciMLBase, Distributions, Statistics
+import SciMLExpectations: build_integrand, ExpectationProblem, SystemMap, Koopman, MonteCarlo,
+                          ExpectationSolution, GenericDistribution
+import Integrals: BatchIntegralFunction
+
+const LIB = get(ENV, "B200E_LIB", "libb200expect.so")
+
+struct PdfDim            # b200e_pdf_dim
+    kind::Int32; _pad::Int32
+    lo::Float64; hi::Float64; mu::Float64; sigma::Float64
+end
+struct CModel            # b200e_model (field order = include/b200_expect.h)
+    struct_size::UInt32
+    nstate::Int32; nparam::Int32; nx::Int32; nout::Int32
+    solver::Int32; n_kkl::Int32; fp_mode::Int32
+    source::Cstring
+    u0::Ptr{Float64}; p::Ptr{Float64}
+    t0::Float64; t1::Float64; abstol::Float64; reltol::Float64; dtmax::Float64; dt_fixed::Float64
+    maxiters::Int64
+    pdf::Ptr{PdfDim}
+    n_devices::Int32; devices::Ptr{Int32}
+    block_size::Int32; blocks_per_sm::Int32; refill_threshold::Int32; chunk_points::Int32
+    cache_dir::Cstring
+end
+struct Counters; nf::UInt64; naccept::UInt64; nreject::UInt64; nfail::UInt64; end
+
+"CUDA sources of the closures the hot path needs (dialect: csrc/kernels/expect_prelude.cuh)."
+Base.@kwdef struct B200Model
+    rhs::String                      # B200E_FN void rhs(real* du, const real* u, const real* p, real t)
+    hmap::String                     # B200E_FN void hmap(const real* x, const real* u0n, const real* pn, real* u0, real* p)
+    observable::String               # B200E_FN void observable(const real* u_end, const real* p, real t_end, real* out)
+    nout::Int
+end
+
+Base.@kwdef struct EnsembleB200 <: SciMLBase.EnsembleAlgorithm
+    model::B200Model
+    devices::Vector{Int32} = Int32[]           # empty: current device; several: sharded + one NCCL all-reduce
+    fp32::Bool = false
+end
+
+pdfdim(d::Uniform) = PdfDim(1, 0, minimum(d), maximum(d), 0.0, 1.0)
+pdfdim(d::Normal) = PdfDim(2, 0, -Inf, Inf, mean(d), std(d))
+pdfdim(d::Truncated{<:Normal}) = PdfDim(3, 0, minimum(d), maximum(d), mean(d.untruncated), std(d.untruncated))
+pdfdim(d) = error("B200Expectations: no device pdf table for $(typeof(d)); supported: Uniform, Normal, truncated(Normal)")
+
+check(rc, h) = rc == 0 ? nothing :
+    error("libb200expect: ", unsafe_string(ccall((:b200e_last_error, LIB), Cstring, (Ptr{Cvoid},), h)), " (status $rc)")
+
+"b200e_create for `exprob` (factors of the product density come from the keyword `dists`)."
+function create_handle(exprob::ExpectationProblem, dists)
+    S = exprob.S; prob = S.prob; ens = S.ensemblealg; m = ens.model
+    u0 = collect(Float64, prob.u0); p = collect(Float64, prob.p)
+    pdf = PdfDim[pdfdim(d) for d in dists]
+    src = m.rhs * "\n" * m.hmap * "\n" * m.observable
+    kw = S.kwargs
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve u0 p pdf src ens begin
+        cm = CModel(sizeof(CModel), length(u0), length(p), length(pdf), m.nout, 0, 0, ens.fp32 ? 1 : 0,
+                    Base.unsafe_convert(Cstring, src), pointer(u0), pointer(p),
+                    prob.tspan[1], prob.tspan[2], get(kw, :abstol, 1e-6), get(kw, :reltol, 1e-3),
+                    get(kw, :dtmax, 0.0), 0.0, get(kw, :maxiters, 100000), pointer(pdf),
+                    length(ens.devices), isempty(ens.devices) ? Ptr{Int32}(C_NULL) : pointer(ens.devices),
+                    0, 0, 0, 0, Cstring(C_NULL))
+        rc = ccall((:b200e_create, LIB), Cint, (Ref{CModel}, Ref{Ptr{Cvoid}}), cm, h)
+        rc == 0 || error("b200e_create: ", unsafe_string(ccall((:b200e_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    end
+    return h[]
+end
+
+const B200Problem = ExpectationProblem{<:SystemMap{<:Any, <:Any, <:EnsembleB200}}
+
+# ---- Koopman batch integrand (reference src/expectation.jl:169-200) --------------------------------
+function build_integrand(prob::B200Problem, ::Koopman, mid, p, batch::Integer; dists = prob.d.pdf_func.dists)  # the product constructor's closure captures `dists` (distribution_utils.jl:41-42)
+    h = create_handle(prob, dists)
+    nout = prob.S.ensemblealg.model.nout
+    function integrand_koopman_systemmap_batch!(dx, x, _)
+        npts = size(x)[end]                       # x :: dim x npts, column-major == point-major layout 0
+        check(ccall((:b200e_eval_nodes, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Float64}),
+                    h, x, npts, 0, 1, dx), h)     # weight_by_pdf = 1: g(sol,p) * pdf(d, x[:, i])
+        return nothing
+    end
+    prototype = nout == 1 ? zeros(1) : zeros(nout, 1)
+    integrand_koopman_systemmap_batch!(prototype, reshape(collect(mid), size(mid)..., 1), p)   # :197-198
+    return BatchIntegralFunction{true}(integrand_koopman_systemmap_batch!, prototype; max_batch = batch)
+end
+
+# ---- MonteCarlo (reference src/expectation.jl:268-294) ---------------------------------------------
+function SciMLBase.solve(exprob::B200Problem, expalg::MonteCarlo; dists = exprob.d.pdf_func.dists, block = 1 << 20)
+    h = create_handle(exprob, dists)
+    nout = exprob.S.ensemblealg.model.nout
+    total = zeros(nout); s = zeros(nout); s2 = zeros(nout); c = Ref(Counters(0, 0, 0, 0))
+    done = 0; n = expalg.trajectories
+    while done < n
+        m = min(block, n - done)
+        x = reduce(hcat, (rand(exprob.d) for _ in 1:m))          # dim x m: host-generated sample set
+        check(ccall((:b200e_reduce_samples, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ref{Counters}),
+                    h, x, m, 0, 0, s, s2, c), h)                   # weight 1, as expectation.jl:282
+        c[].nfail > 0 && @warn "libb200expect: $(c[].nfail) trajectories aborted (maxiters / non-finite / dt underflow)"
+        total .+= s; done += m
+    end
+    ccall((:b200e_destroy, LIB), Cint, (Ptr{Cvoid},), h)
+    u = total ./ n                                                 # mean(sol.u), expectation.jl:293
+    return ExpectationSolution(nout == 1 ? u[1] : u, nothing, nothing)
+end
+
+# ---- structured h / g source generators --------------------------------------------------------------
+hmap_scatter(; u0 = Pair{Int,Int}[], p = Pair{Int,Int}[]) =     # u0 = [i => j]: u0[i] = x[j]  (1-based in, 0-based out)
+    "B200E_FN void hmap(const real* x, const real* u0_nom, const real* p_nom, real* u0, real* p) {\n" *
+    join(["  u0[$(i-1)] = x[$(j-1)];\n" for (i, j) in u0]) * join(["  p[$(i-1)] = x[$(j-1)];\n" for (i, j) in p]) * "}\n"
+observable_components(idx) =                                    # g(sol,p) = sol[idx, end]
+    "B200E_FN void observable(const real* u, const real* p, real t_end, real* out) {\n" *
+    join(["  out[$(k-1)] = u[$(i-1)];\n" for (k, i) in enumerate(idx)]) * "}\n"
+
+export EnsembleB200, B200Model, hmap_scatter, observable_components
+end # module
