@@ -110,20 +110,29 @@ def make_samples(model: str, n: int, seed: int, first_block: int, out: np.ndarra
         b += 1
 
 
+def host_cores() -> int:
+    """Threads the CPU arm uses: every core this process may run on (torchrun exports
+    OMP_NUM_THREADS=1, which must not throttle the reference arm, so the count is passed explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_restatement_rate(model: str, n_sample: int, seed: int = 7, reps: int = 1, x=None):
     """Times the oracle (CPU restatement of the reference path) on all host cores.  Returns
     (evals/s, cores, n, seconds)."""
     import oracle
     orc = oracle.OracleProblem.builtin(model)
-    cores = oracle.max_threads()
+    cores = host_cores()
     if x is None:
         x = np.empty((n_sample, orc.nx))
         make_samples(model, n_sample, seed, 0, x)
     x = x[:n_sample]
-    orc.reduce_samples(x[: min(n_sample, 1 << 16)])  # warm-up (page in, spin threads)
+    orc.reduce_samples(x[: min(n_sample, 1 << 16)], nthreads=cores)  # warm-up (page in, spin threads)
     t0 = time.perf_counter()
     for _ in range(reps):
-        orc.reduce_samples(x)
+        orc.reduce_samples(x, nthreads=cores)
     dt = time.perf_counter() - t0
     return n_sample * reps / dt, cores, n_sample, dt
 
@@ -135,22 +144,22 @@ def run_reference(args):
     model, n_full, desc = WORKLOADS[args.workload]
     import oracle
     orc = oracle.OracleProblem.builtin(model)
-    cores = oracle.max_threads()
+    cores = host_cores()
     # bounded sample per step: ~2 s of CPU work, calibrated on a small block
     x_cal = np.empty((1 << 17, orc.nx))
     make_samples(model, len(x_cal), 7, 0, x_cal)
-    orc.reduce_samples(x_cal)
+    orc.reduce_samples(x_cal, nthreads=cores)
     t0 = time.perf_counter()
-    orc.reduce_samples(x_cal)
+    orc.reduce_samples(x_cal, nthreads=cores)
     rate = len(x_cal) / (time.perf_counter() - t0)
     n = int(min(n_full, max(1 << 17, rate * 2.0)))
     x = np.empty((n, orc.nx))
     make_samples(model, n, 7, 0, x)
     for _ in range(args.warmup):
-        orc.reduce_samples(x)
+        orc.reduce_samples(x, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        s, s2, c = orc.reduce_samples(x)
+        s, s2, c = orc.reduce_samples(x, nthreads=cores)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
     line = {

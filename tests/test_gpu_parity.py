@@ -326,3 +326,25 @@ def test_process_noise_koopman_vs_montecarlo(gpu):
     assert np.allclose(mc.u, want, rtol=1e-2), (mc.u, want)
     assert mc.counters["nfail"] == 0 and mc.counters["nf"] == 1_000_000 * 1024
     ex.close()
+
+
+def test_single_process_multi_device_sharding(gpu):
+    """n_devices > 1 inside one process (the Julia caller's mode): contiguous shards, one NCCL all-reduce
+    of 2*nout sums + 4 counters.  Same integers and (to rounding) the same sums as one device; node
+    outputs bit-identical (each GPU copies its slice of dx back, no collective)."""
+    nd = gpu.device_count()
+    if nd < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    name = "lorenz63"
+    x = sample_points(name, 300007, seed=12)
+    with gpu.Handle(gpu.models.builtin(name, devices=[0])) as h:
+        s1, q1, c1 = h.reduce_samples(x)
+        d1 = h.eval_nodes(x)
+    devs = list(range(min(nd, 8)))
+    with gpu.Handle(gpu.models.builtin(name, devices=devs, chunk_points=50000)) as h:
+        s, q, c = h.reduce_samples(x)
+        d = h.eval_nodes(x)
+        cn = h.last_counters()
+    assert c == c1 and cn == c1
+    assert np.allclose(s, s1, rtol=1e-12) and np.allclose(q, q1, rtol=1e-12)
+    assert np.array_equal(d, d1)
