@@ -137,6 +137,57 @@ def cpu_restatement_rate(model: str, n_sample: int, seed: int = 7, reps: int = 1
     return n_sample * reps / dt, cores, n_sample, dt
 
 
+KOOPMAN_CASES = {
+    # name: (model, lb, ub, ODE tol, ireltol=iabstol, maxevals) -- "wall time per Expectation solve" (BASELINE metric)
+    "koopman_readme_linear2": ("linear2", [1.0, 0.0], [10.0, 6.0], None, 1e-3, 1_000_000),       # configs[0], README.md:57-61
+    "koopman_lotka_volterra": ("lotka_volterra", [1.0, 0.5, 2.0, 0.5], [2.0, 1.5, 4.0, 1.5], 1e-8, 2e-5, 3_000_000),  # configs[2]
+}
+
+
+def time_koopman_solves(arm: str, reps: int = 3):
+    """Wall time of whole Koopman Expectation solves: the restated hcubature_v driver on the host, the
+    batched integrand on the GPU (arm 'b200', through b200e_eval_nodes) or on the host cores (arm 'cpu',
+    oracle).  Both arms see the same node batches."""
+    import scimlexpectations_jl_b200 as sme
+    out = {}
+    for name, (model, lb, ub, otol, itol, maxevals) in KOOPMAN_CASES.items():
+        kw = {} if otol is None else {"abstol": otol, "reltol": otol}
+        if arm == "b200":
+            h = sme.Handle(sme.models.builtin(model, **kw))
+            f = lambda x: h.eval_nodes(x, weight_by_pdf=True)  # noqa: E731
+        else:
+            import oracle
+            orc = oracle.OracleProblem.builtin(model, **kw)
+            nth = host_cores()
+            f = lambda x: orc.eval_nodes(x, weight_by_pdf=True, nthreads=nth)[0]  # noqa: E731
+        nout = 2 if model == "linear2" else 1
+        best, res = None, None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            res = sme.hcubature_v(f, lb, ub, fdim=nout, reltol=itol, abstol=itol, maxevals=maxevals)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out[name] = {"wall_ms": best * 1e3, "u": res.u.tolist(), "resid": res.resid.tolist(), "nevals": res.nevals,
+                     "rounds": res.nrounds, "max_batch": max(res.batch_sizes), "converged": res.converged,
+                     "ode_tol": otol or "default 1e-6/1e-3", "ireltol": itol,
+                     "driver": "hcubature_v restated on the host (cubature.py), integrand per round through "
+                               + ("b200e_eval_nodes" if arm == "b200" else "the oracle (OpenMP)")}
+        if arm == "b200":
+            # the same solve as ONE C call: heap in the library, Genz-Malik rule on the device
+            bestd = None
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                u, resid, st = h.koopman_solve(lb, ub, reltol=itol, abstol=itol, maxevals=maxevals)
+                dt = time.perf_counter() - t0
+                bestd = dt if bestd is None else min(bestd, dt)
+            out[name + "_device_rule"] = {"wall_ms": bestd * 1e3, "u": u.tolist(), "resid": resid.tolist(),
+                                          "nevals": st["nevals"], "rounds": st["nrounds"], "max_batch": st["max_batch"],
+                                          "converged": bool(st["converged"]), "kernel_ms": st["kernel_ms"],
+                                          "driver": "b200e_koopman_solve"}
+            h.close()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -174,6 +225,8 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_solves:
+        line["expectation_solves"] = time_koopman_solves("cpu")
     print(json.dumps(line))
     return 0
 
@@ -303,6 +356,8 @@ def run_b200(args):
             "counters": c, "expectation": mean.tolist(),
             "device_ms_per_step": float(np.mean(total_ms)),
         }
+        if world == 1 and not args.no_solves:
+            line["expectation_solves"] = time_koopman_solves("b200")
         if world == 1 and not args.no_cpu:
             # ~10-20 s of CPU work on the box's host cores
             r0, cores, _, _ = cpu_restatement_rate(model, 1 << 18, x=xp.array)
@@ -334,6 +389,7 @@ def main():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-solves", action="store_true", help="skip the Koopman whole-solve timings")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

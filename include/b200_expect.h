@@ -14,8 +14,11 @@
  *                            (the f!(dx, x, p) Integrals.jl calls once per cubature refinement round)
  *   b200e_reduce_samples  <- solve(exprob, MonteCarlo(n)): the EnsembleProblem solve + mean(sol.u)
  *                                                                             src/expectation.jl:277-293, :304-324
- *   b200e_reduce_regions  <- the Genz-Malik rule Cubature applies to dx (callers either side of the
- *                            path)
+ *   b200e_eval_regions    <- the Genz-Malik rule Cubature's hcubature_v applies to the dx it gets back from
+ *                            the integrand callback (third-party C library behind src/expectation.jl:361-362;
+ *                            SURVEY.md 8f rank 1): regions in, (value, error, split dimension) per region out
+ *   b200e_koopman_solve   <- solve(exprob, Koopman(); quadalg=CubatureJLh(), batch=...)  src/expectation.jl:336-354
+ *                            with hcubature_v's region heap kept inside the library
  *
  * Conventions: every function returns 0 on success and a negative B200E_ERR_* code on failure;
  * b200e_last_error(h) returns a message owned by the library.  All host buffers are caller-owned;
@@ -168,6 +171,30 @@ int b200e_device_alloc(b200e_handle *h, void **dptr, int64_t bytes);
 int b200e_device_free(b200e_handle *h, void *dptr);
 int b200e_memcpy_h2d(b200e_handle *h, void *dptr, const void *src, int64_t bytes);
 int b200e_memcpy_d2h(b200e_handle *h, void *dst, const void *dptr, int64_t bytes);
+
+/* ---- the caller above the path, moved next to it (optional fast path for Koopman) ---------------- */
+typedef struct {
+    double reltol, abstol; /* ireltol / iabstol of solve(exprob, Koopman(); ...) */
+    int64_t maxevals;      /* maxiters of the reference call; <= 0: unlimited */
+} b200e_cubature_opts;
+
+typedef struct {
+    int64_t nevals, nrounds, nregions, max_batch;
+    int32_t converged, _pad;
+    double kernel_ms, total_ms; /* device time of all rounds (CUDA events) / wall time of the solve */
+    b200e_counters counters;    /* summed over all rounds */
+} b200e_cubature_stats;
+
+/* One refinement round: for each region (centre c, half-width w; nx doubles each, region-major) the
+ * device generates the nodes of the Genz-Malik 7/5 rule (Gauss-Kronrod 7/15 for nx == 1), evaluates
+ * g(sol,p)*pdf at each, and returns per region val[nout], err[nout] = |I7 - I5| and the split
+ * dimension (largest summed fourth difference).  Host pointers; blocking. */
+int b200e_eval_regions(b200e_handle *h, const double *centers, const double *halfwidths, int64_t nregions,
+                       double *val, double *err, int32_t *splitdim);
+
+/* Whole h-adaptive solve over the box [lb, ub] (error_norm INDIVIDUAL): u[nout], resid[nout]. */
+int b200e_koopman_solve(b200e_handle *h, const double *lb, const double *ub, const b200e_cubature_opts *opts,
+                        double *u, double *resid, b200e_cubature_stats *stats);
 
 /* FP64 (fp32 != 0: FP32) FMA-chain microbenchmark on the handle's device: the measured
  * roofline denominator for this path (MEASURED_PEAKS.json has no FP64 entry). */

@@ -6,7 +6,7 @@ The directory name contains a dot, so import it through the alias module at the 
 from . import _capi, api, cubature, models  # noqa: F401
 from ._capi import (B200Error, DeviceArray, Handle, ModelSpec, PinnedArray, compile_check, device_count,  # noqa: F401
                     load_library, measure_fma_peak)
-from .api import (EM, BatchIntegralFunction, CubatureJLh, EnsembleB200, ExpectationProblem,  # noqa: F401
+from .api import (EM, B200Cubature, BatchIntegralFunction, CubatureJLh, EnsembleB200, ExpectationProblem,  # noqa: F401
                   ExpectationSolution, GenericDistribution, Koopman, MonteCarlo, Normal, ODEProblem,
                   ProcessNoiseSystemMap, SDEProblem, SystemMap, Truncated, Tsit5, Uniform, build_integrand,
                   extrema, maximum, minimum, pdf, rand, solve, truncated)

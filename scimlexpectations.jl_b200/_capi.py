@@ -34,7 +34,7 @@ EXPORTS = [
     "b200e_compile_log", "b200e_eval_nodes", "b200e_reduce_samples", "b200e_last_counters",
     "b200e_last_stats", "b200e_set_steps_buffer", "b200e_host_alloc", "b200e_host_free",
     "b200e_device_alloc", "b200e_device_free", "b200e_memcpy_h2d", "b200e_memcpy_d2h",
-    "b200e_measure_fma_peak", "b200e_device_count",
+    "b200e_measure_fma_peak", "b200e_device_count", "b200e_eval_regions", "b200e_koopman_solve",
 ]
 
 
@@ -90,6 +90,16 @@ class CallStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class CubatureOpts(C.Structure):
+    _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("maxevals", C.c_int64)]
+
+
+class CubatureStats(C.Structure):
+    _fields_ = [("nevals", C.c_int64), ("nrounds", C.c_int64), ("nregions", C.c_int64), ("max_batch", C.c_int64),
+                ("converged", C.c_int32), ("_pad", C.c_int32), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
+                ("counters", Counters)]
+
+
 _lib = None
 
 
@@ -126,6 +136,9 @@ def load_library():
     L.b200e_memcpy_h2d.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64]
     L.b200e_memcpy_d2h.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64]
     L.b200e_measure_fma_peak.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    L.b200e_eval_regions.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200e_koopman_solve.argtypes = [H, C.c_void_p, C.c_void_p, C.POINTER(CubatureOpts), C.c_void_p, C.c_void_p,
+                                      C.POINTER(CubatureStats)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("b200e_abi_version", "b200e_device_count"):
@@ -434,3 +447,33 @@ class Handle:
                                                 s.ctypes.data, s2.ctypes.data, C.byref(c)))
         del xk
         return s, s2, c.as_dict()
+
+    # -- the caller above the path, on the device --
+    def eval_regions(self, centers, halfwidths):
+        """One cubature refinement round on the device: regions in, ``(val, err, splitdim)`` per region out."""
+        c = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, self.spec.nx)
+        w = np.ascontiguousarray(halfwidths, dtype=np.float64).reshape(-1, self.spec.nx)
+        assert c.shape == w.shape
+        n = len(c)
+        val = np.empty((n, self.spec.nout))
+        err = np.empty((n, self.spec.nout))
+        split = np.empty(n, dtype=np.int32)
+        self._check(self.L.b200e_eval_regions(self._h, c.ctypes.data, w.ctypes.data, n, val.ctypes.data,
+                                              err.ctypes.data, split.ctypes.data))
+        return val, err, split
+
+    def koopman_solve(self, lb, ub, *, reltol=1e-2, abstol=1e-2, maxevals=1000000):
+        """``solve(exprob, Koopman(); quadalg=CubatureJLh(), batch=...)`` as ONE C call: hcubature_v's region
+        heap in the library, Genz-Malik rule applied on the device.  Returns ``(u, resid, stats)``."""
+        lb = np.ascontiguousarray(lb, dtype=np.float64)
+        ub = np.ascontiguousarray(ub, dtype=np.float64)
+        assert lb.shape == ub.shape == (self.spec.nx,)
+        u = np.empty(self.spec.nout)
+        resid = np.empty(self.spec.nout)
+        opts = CubatureOpts(float(reltol), float(abstol), int(maxevals))
+        st = CubatureStats()
+        self._check(self.L.b200e_koopman_solve(self._h, lb.ctypes.data, ub.ctypes.data, C.byref(opts), u.ctypes.data,
+                                               resid.ctypes.data, C.byref(st)))
+        stats = {k: getattr(st, k) for k in ("nevals", "nrounds", "nregions", "max_batch", "converged", "kernel_ms", "total_ms")}
+        stats["counters"] = st.counters.as_dict()
+        return u, resid, stats

@@ -318,6 +318,14 @@ class CubatureJLh:
     pass
 
 
+@dataclass(frozen=True)
+class B200Cubature:
+    """The same h-adaptive Genz-Malik algorithm with the region heap inside libb200expect and the rule
+    applied on the device (``b200e_koopman_solve``): regions go up, (value, error, split dimension) per
+    region come back -- no ``nout x npts`` round trip per refinement round."""
+    pass
+
+
 class BatchIntegralFunction:
     """``BatchIntegralFunction{true}(f!, prototype; max_batch)`` of the reference (expectation.jl:199)."""
 
@@ -365,9 +373,14 @@ def solve(prob: ExpectationProblem, expalg, *, maxiters: int = 1000000, batch: O
         raise TypeError(f"unknown expectation algorithm {expalg!r}")
     if quadalg is None:
         quadalg = CubatureJLh()
-    if not isinstance(quadalg, CubatureJLh):
-        raise NotImplementedError("the batched B200 path is driven by CubatureJLh()")
     lb, ub = extrema(prob.d)
+    if isinstance(quadalg, B200Cubature):
+        if batch is None:
+            raise NotImplementedError("pass batch=<int>: the device path is the batched integrand")
+        u, resid, stats = prob.handle().koopman_solve(lb, ub, reltol=ireltol, abstol=iabstol, maxevals=maxiters)
+        return ExpectationSolution(u[0] if prob.nout == 1 else u, resid[0] if prob.nout == 1 else resid, stats)
+    if not isinstance(quadalg, CubatureJLh):
+        raise NotImplementedError("the batched B200 path is driven by CubatureJLh() or B200Cubature()")
     integrand = build_integrand(prob, expalg, (lb + ub) / 2.0, prob.params, batch)
     nout = prob.nout
 

@@ -19,7 +19,7 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol(sme):
     L = sme.load_library()
     names = _declared_symbols()
-    assert len(names) >= 19
+    assert len(names) >= 21
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/b200_expect.h but not exported"
     assert sorted(sme._capi.EXPORTS) == names
@@ -32,6 +32,7 @@ def test_struct_layout_matches_header(sme):
     assert C.sizeof(sme._capi.Counters) == 32
     assert C.sizeof(sme._capi.CallStats) == 64
     assert C.sizeof(sme._capi.Model) == 160
+    assert C.sizeof(sme._capi.CubatureOpts) == 24 and C.sizeof(sme._capi.CubatureStats) == 88
 
 
 def test_compile_check_all_builtin_models_for_sm100a(sme, tmp_path):

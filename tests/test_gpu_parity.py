@@ -348,3 +348,61 @@ def test_single_process_multi_device_sharding(gpu):
     assert c == c1 and cn == c1
     assert np.allclose(s, s1, rtol=1e-12) and np.allclose(q, q1, rtol=1e-12)
     assert np.array_equal(d, d1)
+
+
+def test_device_side_genz_malik_regions(gpu):
+    """regions in, (value, error, split dimension) per region out.  Checked against the
+    host twin of the rule (cubature.py) applied to ORACLE node values of the same regions."""
+    from scimlexpectations_jl_b200.cubature import make_rule
+    rng = np.random.default_rng(3)
+    for name, lb, ub in (("linear2", [1.0, 0.0], [10.0, 6.0]), ("lotka_volterra", [1.0, 0.5, 2.0, 0.5], [2.0, 1.5, 4.0, 1.5]),
+                         ("lorenz63", [9.0, 25.2, 2.4, 0.6, -0.4, -0.4], [11.0, 30.8, 2.9333, 1.4, 0.4, 0.4]),
+                         ("decay1", [0.5], [1.5])):
+        lb, ub = np.array(lb), np.array(ub)
+        dim = len(lb)
+        nreg = 37
+        hw = (ub - lb) * rng.uniform(0.02, 0.25, (nreg, dim))
+        c = lb + hw + (ub - lb - 2 * hw) * rng.uniform(0, 1, (nreg, dim))
+        rule = make_rule(dim)
+        orc = oracle.OracleProblem.builtin(name)
+        f, cref = orc.eval_nodes(np.ascontiguousarray(rule.nodes(c, hw)), weight_by_pdf=True)
+        val_r, err_r, split_r = rule.apply(f.reshape(nreg, rule.num_points, -1), hw)
+        with gpu.Handle(gpu.models.builtin(name)) as h:
+            val, err, split = h.eval_regions(c, hw)
+            assert h.last_counters() == cref
+            assert h.last_stats()["h2d_bytes"] == 2 * nreg * dim * 8
+        scale = np.abs(val_r).max()
+        assert np.max(np.abs(val - val_r)) <= 1e-9 * scale, name
+        assert np.max(np.abs(err - err_r)) <= 1e-8 * np.abs(err_r).max() + 1e-12 * scale, name
+        assert np.array_equal(split, split_r), name
+
+
+def test_koopman_solve_in_library_matches_host_driver(gpu):
+    """b200e_koopman_solve (heap in the library, rule on the device) against the host twin of hcubature_v
+    driven by the oracle: same number of evaluations and rounds, u and resid within 1e-8, README digits."""
+    cases = [("linear2", [1.0, 0.0], [10.0, 6.0], {}, 1e-3), ("decay1", [0.5], [1.5], {}, 1e-6),
+             ("lotka_volterra", [1.0, 0.5, 2.0, 0.5], [2.0, 1.5, 4.0, 1.5], {"abstol": 1e-8, "reltol": 1e-8}, 1e-4),
+             ("lotka_volterra", [1.0, 0.5, 2.0, 0.5], [2.0, 1.5, 4.0, 1.5], {}, 1e-2)]
+    for name, lb, ub, kw, tol in cases:
+        orc = oracle.OracleProblem.builtin(name, **kw)
+        nout = orc.nout
+        ref = gpu.hcubature_v(lambda x: orc.eval_nodes(x, weight_by_pdf=True)[0], lb, ub, fdim=nout, reltol=tol, abstol=tol,
+                              maxevals=400000)
+        with gpu.Handle(gpu.models.builtin(name, **kw)) as h:
+            u, resid, st = h.koopman_solve(lb, ub, reltol=tol, abstol=tol, maxevals=400000)
+        assert (st["nevals"], st["nrounds"], st["nregions"], bool(st["converged"])) == (ref.nevals, ref.nrounds, ref.nregions, ref.converged), (name, st)
+        assert np.max(np.abs(u - ref.u) / np.abs(ref.u)) < 1e-8, (name, u, ref.u)
+        assert np.max(np.abs(resid - ref.resid) / np.abs(ref.resid)) < 1e-6, (name, resid, ref.resid)
+        assert st["counters"]["nfail"] == 0 and st["counters"]["naccept"] > 0
+        if name == "linear2":
+            assert np.allclose(u, README["koopman_u"], rtol=0, atol=2e-9)
+            assert np.allclose(resid, README["koopman_resid"], rtol=0, atol=1e-10)
+    # through the mirrored public API
+    m = gpu.models
+    prob = gpu.ODEProblem(m._LINEAR2_RHS, [1.0, 1.0], (0.0, 3.0), [1.0, 2.0])
+    smap = gpu.SystemMap(prob, gpu.Tsit5(), gpu.EnsembleB200())
+    gd = gpu.GenericDistribution(gpu.Uniform(1, 10), gpu.truncated(gpu.Normal(3, 1), 0, 6))
+    ex = gpu.ExpectationProblem(smap, m.observable_components([0, 1]), m.hmap_scatter(u0_from_x=[(0, 0), (1, 1)]), gd, nout=2)
+    sol = gpu.solve(ex, gpu.Koopman(), batch=100, quadalg=gpu.B200Cubature(), ireltol=1e-3, iabstol=1e-3)
+    assert np.allclose(sol.u, README["koopman_u"], rtol=0, atol=2e-9) and sol.original["nevals"] == 119
+    ex.close()
