@@ -196,7 +196,7 @@ constexpr double ln10_04 = 0.4 * 2.302585092994045684;
 struct b200e_consts {
     double c1, c2, c3, c4, a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, a71,
         a72, a73, a74, a75, a76, bt1, bt2, bt3, bt4, bt5, bt6, bt7;
-    double hb1, hb2, gamma, qmin, qmax, le2_qoldinit, inv_n, e2_lo, e2_hi;
+    double hb1, hb2, gamma, qmin, qmax, le2_qoldinit, inv_n;
     double ln2_hi, ln2_lo, ln2, log2e, rnd_magic, ln10_04;
     double lg[10];  // atanh series 2/(2k+1), k = 0..9
     double ex[13];  // 1/k!, k = 0..12
@@ -206,7 +206,7 @@ __constant__ b200e_consts KC = {
     lit::c1, lit::c2, lit::c3, lit::c4, lit::a21, lit::a31, lit::a32, lit::a41, lit::a42, lit::a43, lit::a51,
     lit::a52, lit::a53, lit::a54, lit::a61, lit::a62, lit::a63, lit::a64, lit::a65, lit::a71, lit::a72, lit::a73,
     lit::a74, lit::a75, lit::a76, lit::bt1, lit::bt2, lit::bt3, lit::bt4, lit::bt5, lit::bt6, lit::bt7,
-    lit::hb1, lit::hb2, lit::gamma, lit::qmin, lit::qmax, lit::le2_qoldinit, lit::inv_n, lit::e2_lo, lit::e2_hi,
+    lit::hb1, lit::hb2, lit::gamma, lit::qmin, lit::qmax, lit::le2_qoldinit, lit::inv_n,
     lit::ln2_hi, lit::ln2_lo, lit::ln2, lit::log2e, lit::rnd_magic, lit::ln10_04,
     {2.0, 2.0 / 3, 2.0 / 5, 2.0 / 7, 2.0 / 9, 2.0 / 11, 2.0 / 13, 2.0 / 15, 2.0 / 17, 2.0 / 19},
     {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
@@ -377,9 +377,9 @@ struct Lane {
     unsigned nf0, nacc, nrej;  // nf = nf0 (initial-step evaluations) + 6 * (nacc + nrej)
 };
 
-__device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dtmax, const real abstol,
-                                           const real reltol, const real snap_tol, const int maxiters,
-                                           const real one_plus_eps) {
+__device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dtmax, const bool clip_dtmax,
+                                           const real abstol, const real reltol, const real snap_tol,
+                                           const int maxiters, const real one_plus_eps) {
     real *u = L.u, *k1 = L.k1, *p = L.p;
     const real t = L.t;
     // ---- loopheader!: a NaN error estimate in the previous attempt, the iteration cap, or a step
@@ -444,13 +444,15 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     // ---- PI controller in log space on e2: one log + one exp instead of two pow + sqrt ----
     // accept:  1/q = gamma * qold^b2 / EEst^b1  clamped to [qmin, qmax]
     // reject:  dt *= max(qmin, gamma / EEst^b1)  (< 1, so the same clamp applies)
-    // Outside [e2_lo, e2_hi] the clamps decide alone, so e2 is clamped first and the log never
-    // sees 0, inf or a subnormal.
-    const real le2 = log_pos(pmin(pmax(e2, K_(e2_lo)), K_(e2_hi)));
+    // No special cases: log_pos maps e2 = 0 / subnormal to about -709 and e2 = +inf to +710, for
+    // which the clamps on 1/q decide alone exactly as the reference's (EEst == 0 -> q = 1/qmax;
+    // EEst = Inf -> dt/5), and |b2*le2old - b1*le2| <= 50 stays far inside exp_small's range.
+    const real le2 = log_pos(e2);
     const real hist = accept ? L.le2old : R_(0.0);
     real qinv = K_(gamma) * exp_small(fma(K_(hb2), hist, -K_(hb1) * le2));
     qinv = pmin(K_(qmax), pmax(K_(qmin), qinv));
-    L.dt = pmin(dtmax, dt * qinv);
+    L.dt = dt * qinv;
+    if (clip_dtmax) L.dt = pmin(dtmax, L.dt);  // warp-uniform; only when the caller set dtmax < t1 - t0
     if (accept) {
         L.le2old = fmax(le2, K_(le2_qoldinit));  // qold = max(EEst, 1e-4)
         real tn = t + dt;
@@ -482,6 +484,8 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     const real abstol = (real)P.abstol, reltol = (real)P.reltol;
     const real snap_tol = (real)P.snap_tol;
     const int maxiters = (int)P.maxiters;
+    // the clip to the end point (dt <= t1 - t) already enforces the default dtmax = t1 - t0
+    const bool clip_dtmax = P.dtmax < P.t1 - P.t0;
 #if B200E_FP32
     const real one_plus_eps = R_(1.0) + R_(1.1920928955078125e-07);
 #else
@@ -517,7 +521,7 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
         if (act_m == 0u) continue;
         // ---- step phase: a tight loop, one vote per step, until some lane finishes ----
         do {
-            if (L.state == LANE_ACTIVE) tsit5_step(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps);
+            if (L.state == LANE_ACTIVE) tsit5_step(L, t1, dtmax, clip_dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps);
         } while (__ballot_sync(B200E_FULL, L.state == LANE_ACTIVE) == act_m);
     }
     block_reduce_store<REDUCE>(P, A);

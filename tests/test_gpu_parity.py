@@ -406,3 +406,28 @@ def test_koopman_solve_in_library_matches_host_driver(gpu):
     sol = gpu.solve(ex, gpu.Koopman(), batch=100, quadalg=gpu.B200Cubature(), ireltol=1e-3, iabstol=1e-3)
     assert np.allclose(sol.u, README["koopman_u"], rtol=0, atol=2e-9) and sol.original["nevals"] == 119
     ex.close()
+
+
+def test_non_finite_inputs_are_contained(gpu):
+    """NaN / Inf sample points poison only their own column: the trajectory is counted as failed (the
+    reference would carry a failed retcode), every other node is bit-identical to a clean batch."""
+    name = "lorenz63"
+    x = sample_points(name, 4096, seed=13)
+    with gpu.Handle(gpu.models.builtin(name)) as h:
+        clean = h.eval_nodes(x, weight_by_pdf=False)
+        c_clean = h.last_counters()
+        bad = x.copy()
+        bad[7, 3] = np.nan       # u0[0] = NaN
+        bad[100, 0] = np.inf     # sigma = Inf
+        bad[2049, 4] = -np.inf   # u0[1] = -Inf
+        dirty = h.eval_nodes(bad, weight_by_pdf=False)
+        c_dirty = h.last_counters()
+        s, s2, c_red = h.reduce_samples(bad)
+    rows = np.array([7, 100, 2049])
+    mask = np.ones(len(x), dtype=bool)
+    mask[rows] = False
+    assert np.array_equal(dirty[mask], clean[mask])
+    assert not np.all(np.isfinite(dirty[rows]))
+    assert c_dirty["nfail"] == 3 and c_clean["nfail"] == 0 and c_red["nfail"] == 3
+    orc = oracle.OracleProblem.builtin(name)
+    assert orc.eval_nodes(bad, weight_by_pdf=False)[1]["nfail"] == 3
