@@ -340,7 +340,7 @@ def run_b200(args):
                        "samples_per_gpu_per_step": n, "sample_set": f"PCG64(SeedSequence([{args.seed}, block])), blocks of 2^20",
                        "l2": f"input {n * nx * 8 / 1e6:.0f} MB per GPU > 126 MB L2" if n * nx * 8 > 126e6 else "input smaller than L2",
                        "grid": st["grid"], "block": st["block"], "regs": st["regs_per_thread"],
-                       "refill_threshold": args.refill or 32, "parallelism": f"samples sharded over {world} GPU(s)"},
+                       "refill_threshold": args.refill or "auto", "parallelism": f"samples sharded over {world} GPU(s)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(ste["h2d_bytes"]),
                     "d2h_bytes_per_step": int(ste["d2h_bytes"]), "ms_per_step": Te / e_steps * 1e3,

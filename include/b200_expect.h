@@ -101,9 +101,9 @@ typedef struct {
     /* placement and launch shape (0 = library default) */
     int32_t n_devices;        /* 0/1: single device */
     const int32_t *devices;   /* CUDA ordinals; NULL -> current device (n_devices<=1) or 0..n-1 */
-    int32_t block_size;       /* threads per block, multiple of 32 */
+    int32_t block_size;       /* threads per block, multiple of 32 (default 256) */
     int32_t blocks_per_sm;    /* resident blocks per SM to launch (grid = SMs * this) */
-    int32_t refill_threshold; /* lanes of a warp that must be idle before the warp reloads (1..32) */
+    int32_t refill_threshold; /* lanes of a warp that must be idle before the warp reloads (1..32); 0 = automatic */
     int32_t chunk_points;     /* host-pointer calls are pipelined in chunks of this many points */
     const char *cache_dir;    /* cubin cache directory, NULL -> $B200E_CACHE_DIR or disabled */
 } b200e_model;

@@ -62,7 +62,7 @@ __device__ __forceinline__ void load_point(const b200e_kparams &P, long long i, 
 // TRAJECTORY (not per step), so they live in shared memory, one conflict-free column per thread,
 // and stay out of the register budget of the step loop (registers decide how many warps are
 // resident, and resident warps are what hides the FP64 dependency chains).
-constexpr bool ACC_SMEM = (NACC * 8 + 4 * 8) * B200E_BLOCK <= 16384;
+constexpr bool ACC_SMEM = (NACC * 8 + 4 * 8) * B200E_BLOCK <= 32768;
 __shared__ double sh_acc[ACC_SMEM ? NACC : 1][B200E_BLOCK];
 __shared__ unsigned long long sh_cnt[ACC_SMEM ? 4 : 1][B200E_BLOCK];
 
@@ -492,6 +492,14 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     const real one_plus_eps = R_(1.0) + R_(2.220446049250313e-16);
 #endif
 
+    // refill policy: an explicit threshold (1..32), or 0 = automatic: the first generation of 32
+    // trajectories runs to its slowest lane; if that left the warp idle for more than a fifth of the
+    // lane-steps (max > 1.25 mean attempted steps) the warp re-loads whenever 8 lanes are idle from
+    // then on, otherwise it keeps starting 32 trajectories together.  Sample -> lane ownership does
+    // not depend on the policy, so results and counters are identical either way.
+    int thr_eff = P.refill_threshold > 0 ? P.refill_threshold : 32;
+    bool tune = P.refill_threshold <= 0;
+
     for (;;) {
         // ---- refill phase: runs only when the set of stepping lanes has changed ----
         const bool wants = (L.state == LANE_DONE) || (L.state == LANE_EMPTY && next < P.npts);
@@ -499,8 +507,15 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
         unsigned act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
         if ((idle_m | act_m) == 0u) break;
         const int live = __popc(idle_m | act_m);
-        const int thr = P.refill_threshold < live ? P.refill_threshold : live;
+        const int thr = thr_eff < live ? thr_eff : live;
         if (__popc(idle_m) >= thr) {  // warp-uniform
+            const unsigned done_m = __ballot_sync(B200E_FULL, L.state == LANE_DONE);
+            if (tune && done_m == B200E_FULL) {  // first full generation finished: measure its imbalance
+                const unsigned st = L.nacc + L.nrej;
+                const unsigned mx = __reduce_max_sync(B200E_FULL, st), sm = __reduce_add_sync(B200E_FULL, st);
+                if (mx * 128u > sm * 5u) thr_eff = 8;  // max > 1.25 * mean
+                tune = false;
+            }
             if (wants) {
                 if (L.state == LANE_DONE) {
                     emit<REDUCE>(P, cur, L.u, L.p, wgt, A);
