@@ -178,13 +178,20 @@ constexpr double bt1 = -0.00178001105222577714, bt2 = -0.0008164344596567469,
 // PI controller on e2 = EEst^2:  EEst^b1 = e2^(b1/2)
 constexpr double hb1 = 0.5 * 7.0 / 50.0, hb2 = 0.5 * 2.0 / 25.0;
 constexpr double gamma = 9.0 / 10.0, qmin = 1.0 / 5.0, qmax = 10.0;
+constexpr double ln_gamma = -0.10536051565782630123;  // log(9/10)
 constexpr double le2_qoldinit = -18.420680743952364;  // log(1e-4^2)
 constexpr double inv_n = 1.0 / B200E_NSTATE;
 // below / above these e2 the clamps decide alone (q = 1/qmax resp. reject factor = qmin):
 //   gamma * e2^-hb1 >= qmax  <=>  e2 <= (gamma/qmax)^(1/hb1) = 1.2e-15 ;  take 1e-30 for margin
 //   gamma * e2^-hb1 <= qmin  <=>  e2 >= (gamma/qmin)^(1/hb1) = 2.1e9   ;  take 1e12 for margin
 constexpr double e2_lo = 1e-30, e2_hi = 1e12;
-constexpr double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+// ln 2 = ln2_hi + ln2_lo with ln2_hi on 21 bits: n * ln2_hi is exact and ln2_hi is a DFMA immediate
+constexpr double ln2_hi = 0x1.62e43p-1, ln2_lo = -0x1.05c610ca86c39p-29;
+// high-order series coefficients rounded to the 21 bits a DFMA immediate carries: their terms are
+// below 2^-32 of the sum, so the 2^-21 rounding stays below 2^-53 (and they cost no uniform register)
+constexpr double lg6i = 0x1.3b13bp-3, lg7i = 0x1.11111p-3, lg8i = 0x1.e1e1ep-4, lg9i = 0x1.af287p-4;
+constexpr double lg5i = 0x1.745d1p-3, ex8i = 0x1.a01ap-16;  // term <= 5e-9 of the sum: error <= 3e-15, the controller needs 1e-13
+constexpr double ex9i = 0x1.71de4p-19, ex10i = 0x1.27e5p-22, ex11i = 0x1.ae645p-26, ex12i = 0x1.1eed9p-29;
 constexpr double ln2 = 0.6931471805599453094, log2e = 1.4426950408889634074;
 constexpr double rnd_magic = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-nearest-integer
 constexpr double ln10_04 = 0.4 * 2.302585092994045684;
@@ -196,7 +203,7 @@ constexpr double ln10_04 = 0.4 * 2.302585092994045684;
 struct b200e_consts {
     double c1, c2, c3, c4, a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, a71,
         a72, a73, a74, a75, a76, bt1, bt2, bt3, bt4, bt5, bt6, bt7;
-    double hb1, hb2, gamma, qmin, qmax, le2_qoldinit, inv_n;
+    double hb1, hb2, ln_gamma, qmin, qmax, le2_qoldinit, inv_n;
     double ln2_hi, ln2_lo, ln2, log2e, rnd_magic, ln10_04;
     double lg[10];  // atanh series 2/(2k+1), k = 0..9
     double ex[13];  // 1/k!, k = 0..12
@@ -206,7 +213,7 @@ __constant__ b200e_consts KC = {
     lit::c1, lit::c2, lit::c3, lit::c4, lit::a21, lit::a31, lit::a32, lit::a41, lit::a42, lit::a43, lit::a51,
     lit::a52, lit::a53, lit::a54, lit::a61, lit::a62, lit::a63, lit::a64, lit::a65, lit::a71, lit::a72, lit::a73,
     lit::a74, lit::a75, lit::a76, lit::bt1, lit::bt2, lit::bt3, lit::bt4, lit::bt5, lit::bt6, lit::bt7,
-    lit::hb1, lit::hb2, lit::gamma, lit::qmin, lit::qmax, lit::le2_qoldinit, lit::inv_n,
+    lit::hb1, lit::hb2, lit::ln_gamma, lit::qmin, lit::qmax, lit::le2_qoldinit, lit::inv_n,
     lit::ln2_hi, lit::ln2_lo, lit::ln2, lit::log2e, lit::rnd_magic, lit::ln10_04,
     {2.0, 2.0 / 3, 2.0 / 5, 2.0 / 7, 2.0 / 9, 2.0 / 11, 2.0 / 13, 2.0 / 15, 2.0 / 17, 2.0 / 19},
     {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
@@ -257,9 +264,9 @@ __device__ __forceinline__ double log_pos(double x) {
     const double z = s * s;
     // Estrin: depth 5 instead of 10 dependent DFMAs (4 resident warps cannot hide a long chain)
     const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
-    const double q01 = fma(K_(lg[1]), z, K_(lg[0])), q23 = fma(K_(lg[3]), z, K_(lg[2]));
-    const double q45 = fma(K_(lg[5]), z, K_(lg[4])), q67 = fma(K_(lg[7]), z, K_(lg[6]));
-    const double q89 = fma(K_(lg[9]), z, K_(lg[8]));
+    const double q01 = fma(K_(lg[1]), z, 2.0), q23 = fma(K_(lg[3]), z, K_(lg[2]));
+    const double q45 = fma(lit::lg5i, z, K_(lg[4])), q67 = fma(lit::lg7i, z, lit::lg6i);
+    const double q89 = fma(lit::lg9i, z, lit::lg8i);
     const double q03 = fma(q23, z2, q01), q47 = fma(q67, z2, q45);
     const double p = fma(q89, z8, fma(q47, z4, q03));
     return fma((double)e, K_(ln2), s * p);
@@ -269,14 +276,14 @@ __device__ __forceinline__ double exp_small(double y) {
     const double t = fma(y, K_(log2e), K_(rnd_magic));
     const int n = __double2loint(t);
     const double nf = t - K_(rnd_magic);
-    double r = fma(-nf, K_(ln2_hi), y);
+    double r = fma(-nf, lit::ln2_hi, y);
     r = fma(-nf, K_(ln2_lo), r);
     const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double q01 = fma(K_(ex[1]), r, K_(ex[0])), q23 = fma(K_(ex[3]), r, K_(ex[2]));
+    const double q01 = r + 1.0, q23 = fma(K_(ex[3]), r, 0.5);
     const double q45 = fma(K_(ex[5]), r, K_(ex[4])), q67 = fma(K_(ex[7]), r, K_(ex[6]));
-    const double q89 = fma(K_(ex[9]), r, K_(ex[8])), qab = fma(K_(ex[11]), r, K_(ex[10]));
+    const double q89 = fma(lit::ex9i, r, lit::ex8i), qab = fma(lit::ex11i, r, lit::ex10i);
     const double q03 = fma(q23, r2, q01), q47 = fma(q67, r2, q45);
-    const double q8c = fma(K_(ex[12]), r4, fma(qab, r2, q89));
+    const double q8c = fma(lit::ex12i, r4, fma(qab, r2, q89));
     const double p = fma(q8c, r8, fma(q47, r4, q03));
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
@@ -435,7 +442,8 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
         const real r = ut * rcp_pos(sc);
         ss = fma(r, r, ss);
     }
-    const real e2 = ss * K_(inv_n);  // EEst^2
+    // 1/N is a DFMA immediate when N is a power of two
+    const real e2 = ss * (((N & (N - 1)) == 0) ? R_(lit::inv_n) : K_(inv_n));  // EEst^2
     // NaN estimate: the reference counts a rejection, dt turns NaN and the solve aborts at the next
     // loop header -- same here through L.failed = 2 (the accept test below is false for a NaN)
     L.failed = (e2 == e2) ? 0 : 2;
@@ -449,8 +457,8 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     // EEst = Inf -> dt/5), and |b2*le2old - b1*le2| <= 50 stays far inside exp_small's range.
     const real le2 = log_pos(e2);
     const real hist = accept ? L.le2old : R_(0.0);
-    real qinv = K_(gamma) * exp_small(fma(K_(hb2), hist, -K_(hb1) * le2));
-    qinv = pmin(K_(qmax), pmax(K_(qmin), qinv));
+    real qinv = exp_small(fma(K_(hb2), hist, fma(-K_(hb1), le2, K_(ln_gamma))));  // gamma * e2old^hb2 / e2^hb1
+    qinv = pmin(R_(lit::qmax), pmax(K_(qmin), qinv));
     L.dt = dt * qinv;
     if (clip_dtmax) L.dt = pmin(dtmax, L.dt);  // warp-uniform; only when the caller set dtmax < t1 - t0
     if (accept) {
