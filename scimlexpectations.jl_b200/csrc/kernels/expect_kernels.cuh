@@ -1,5 +1,6 @@
 // expect_kernels.cuh -- second part of the NVRTC translation unit, placed AFTER the user's model
-// source (rhs / hmap / observable / diffusion are visible here and inline into the loops).
+// source (rhs / hmap / observable / diffusion are visible here and inline into the loops) and after
+// expect_math.cuh.
 //
 // Replaces, for a whole batch per launch, what the reference does per trajectory on a CPU thread:
 //   prob_func   src/expectation.jl:175-178 (MC :277-280, process noise :215-225 / :304-314)
@@ -151,143 +152,9 @@ __device__ __forceinline__ void block_reduce_store(const b200e_kparams &P, Accum
 // ------------------------------------------------------------------------------------------
 // Adaptive Tsit5 (Tsitouras 2011) with OrdinaryDiffEq's defaults: Hairer-Wanner initial step,
 // PI controller beta1=7/50 beta2=2/25 gamma=9/10 qmin=1/5 qmax=10 qoldinit=1e-4, RMS error norm.
-//
-// FP64 instruction economy (ncu, profiles/r1_*): a 64-bit literal costs two UMOVs every time it is
-// used, and CUDA's log/exp/div/sqrt each carry a special-case branch.  So (1) every constant of
-// the step lives in __constant__ memory and is read as a c[bank][off] operand of the DFMA itself,
-// (2) the controller's power function is one branch-free log and one branch-free exp whose
-// coefficients sit in the same table, valid on the clamped domain the controller can reach, and
-// (3) the error scale uses MUFU.RCP64H + two Newton steps instead of an IEEE division.
+// Constants (KC / K_), the table-driven log / exp and the reciprocal live in expect_math.cuh.
 // ------------------------------------------------------------------------------------------
-#define R_(x) ((real)(x))
-
-namespace lit {
-constexpr double c1 = 0.161, c2 = 0.327, c3 = 0.9, c4 = 0.9800255409045097;
-constexpr double a21 = 0.161;
-constexpr double a31 = -0.008480655492356989, a32 = 0.335480655492357;
-constexpr double a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815;
-constexpr double a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365,
-                 a54 = -0.09249506636175525;
-constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.159367898576159,
-                 a64 = -0.071584973281401, a65 = -0.028269050394068383;
-constexpr double a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996,
-                 a74 = 1.379008574103742, a75 = -3.290069515436081, a76 = 2.324710524099774;
-constexpr double bt1 = -0.00178001105222577714, bt2 = -0.0008164344596567469,
-                 bt3 = 0.007880878010261995, bt4 = -0.1447110071732629, bt5 = 0.5823571654525552,
-                 bt6 = -0.45808210592918697, bt7 = 0.015151515151515152;
-// PI controller on e2 = EEst^2:  EEst^b1 = e2^(b1/2)
-constexpr double hb1 = 0.5 * 7.0 / 50.0, hb2 = 0.5 * 2.0 / 25.0;
-constexpr double gamma = 9.0 / 10.0, qmin = 1.0 / 5.0, qmax = 10.0;
-constexpr double ln_gamma = -0.10536051565782630123;  // log(9/10)
-constexpr double le2_qoldinit = -18.420680743952364;  // log(1e-4^2)
-constexpr double inv_n = 1.0 / B200E_NSTATE;
-// below / above these e2 the clamps decide alone (q = 1/qmax resp. reject factor = qmin):
-//   gamma * e2^-hb1 >= qmax  <=>  e2 <= (gamma/qmax)^(1/hb1) = 1.2e-15 ;  take 1e-30 for margin
-//   gamma * e2^-hb1 <= qmin  <=>  e2 >= (gamma/qmin)^(1/hb1) = 2.1e9   ;  take 1e12 for margin
-constexpr double e2_lo = 1e-30, e2_hi = 1e12;
-// ln 2 = ln2_hi + ln2_lo with ln2_hi on 21 bits: n * ln2_hi is exact and ln2_hi is a DFMA immediate
-constexpr double ln2_hi = 0x1.62e43p-1, ln2_lo = -0x1.05c610ca86c39p-29;
-// high-order series coefficients rounded to the 21 bits a DFMA immediate carries: their terms are
-// below 2^-32 of the sum, so the 2^-21 rounding stays below 2^-53 (and they cost no uniform register)
-constexpr double lg6i = 0x1.3b13bp-3, lg7i = 0x1.11111p-3, lg8i = 0x1.e1e1ep-4, lg9i = 0x1.af287p-4;
-constexpr double lg5i = 0x1.745d1p-3, ex8i = 0x1.a01ap-16;  // term <= 5e-9 of the sum: error <= 3e-15, the controller needs 1e-13
-constexpr double ex9i = 0x1.71de4p-19, ex10i = 0x1.27e5p-22, ex11i = 0x1.ae645p-26, ex12i = 0x1.1eed9p-29;
-constexpr double ln2 = 0.6931471805599453094, log2e = 1.4426950408889634074;
-constexpr double rnd_magic = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-nearest-integer
-constexpr double ln10_04 = 0.4 * 2.302585092994045684;
-}  // namespace lit
-
-#if B200E_FP32
-#define K_(name) ((real)lit::name)
-#else
-struct b200e_consts {
-    double c1, c2, c3, c4, a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, a71,
-        a72, a73, a74, a75, a76, bt1, bt2, bt3, bt4, bt5, bt6, bt7;
-    double hb1, hb2, ln_gamma, qmin, qmax, le2_qoldinit, inv_n;
-    double ln2_hi, ln2_lo, ln2, log2e, rnd_magic, ln10_04;
-    double lg[10];  // atanh series 2/(2k+1), k = 0..9
-    double ex[13];  // 1/k!, k = 0..12
-};
-// not `const`: the compiler must read it from the constant bank instead of folding literals back in
-__constant__ b200e_consts KC = {
-    lit::c1, lit::c2, lit::c3, lit::c4, lit::a21, lit::a31, lit::a32, lit::a41, lit::a42, lit::a43, lit::a51,
-    lit::a52, lit::a53, lit::a54, lit::a61, lit::a62, lit::a63, lit::a64, lit::a65, lit::a71, lit::a72, lit::a73,
-    lit::a74, lit::a75, lit::a76, lit::bt1, lit::bt2, lit::bt3, lit::bt4, lit::bt5, lit::bt6, lit::bt7,
-    lit::hb1, lit::hb2, lit::ln_gamma, lit::qmin, lit::qmax, lit::le2_qoldinit, lit::inv_n,
-    lit::ln2_hi, lit::ln2_lo, lit::ln2, lit::log2e, lit::rnd_magic, lit::ln10_04,
-    {2.0, 2.0 / 3, 2.0 / 5, 2.0 / 7, 2.0 / 9, 2.0 / 11, 2.0 / 13, 2.0 / 15, 2.0 / 17, 2.0 / 19},
-    {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
-     1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600}};
-#define K_(name) (KC.name)
-#endif
-
-// ---- branch-free scalar helpers -----------------------------------------------------------
-#if B200E_FP32
-__device__ __forceinline__ float rcp_pos(float b) { return 1.0f / b; }
-__device__ __forceinline__ float log_pos(float x) { return logf(x); }
-__device__ __forceinline__ float exp_small(float y) { return expf(y); }
-__device__ __forceinline__ float sqrt_pos(float x) { return sqrtf(x); }
-#else
-// 1/b for normal b > 0: MUFU.RCP64H seed (~20 bits) + two Newton steps (20 -> 40 -> 80 bits)
-__device__ __forceinline__ double rcp_pos(double b) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    double e = fma(-b, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-b, r, 1.0);
-    return fma(r, e, r);
-}
-// sqrt(x) for normal x > 0: MUFU.RSQ64H seed + two coupled Newton steps (Goldschmidt form)
-__device__ __forceinline__ double sqrt_pos(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double g = x * y, h = 0.5 * y;
-    double r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    const double d = fma(-g, g, x);
-    return fma(d, h, g);
-}
-// log(x) for normal x > 0:  x = 2^e m, m in [sqrt(1/2), sqrt(2));  log m = 2 atanh((m-1)/(m+1))
-__device__ __forceinline__ double log_pos(double x) {
-    int hi = __double2hiint(x), lo = __double2loint(x);
-    int e = (hi >> 20) - 1023;
-    hi = (hi & 0x000fffff) | 0x3ff00000;
-    const int up = hi >= 0x3ff6a09f;  // m >= ~sqrt(2): halve it
-    hi -= up << 20;
-    e += up;
-    const double m = __hiloint2double(hi, lo);
-    const double s = (m - 1.0) * rcp_pos(m + 1.0);
-    const double z = s * s;
-    // Estrin: depth 5 instead of 10 dependent DFMAs (4 resident warps cannot hide a long chain)
-    const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
-    const double q01 = fma(K_(lg[1]), z, 2.0), q23 = fma(K_(lg[3]), z, K_(lg[2]));
-    const double q45 = fma(lit::lg5i, z, K_(lg[4])), q67 = fma(lit::lg7i, z, lit::lg6i);
-    const double q89 = fma(lit::lg9i, z, lit::lg8i);
-    const double q03 = fma(q23, z2, q01), q47 = fma(q67, z2, q45);
-    const double p = fma(q89, z8, fma(q47, z4, q03));
-    return fma((double)e, K_(ln2), s * p);
-}
-// exp(y) for |y| < 700 (no overflow / subnormal handling)
-__device__ __forceinline__ double exp_small(double y) {
-    const double t = fma(y, K_(log2e), K_(rnd_magic));
-    const int n = __double2loint(t);
-    const double nf = t - K_(rnd_magic);
-    double r = fma(-nf, lit::ln2_hi, y);
-    r = fma(-nf, K_(ln2_lo), r);
-    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double q01 = r + 1.0, q23 = fma(K_(ex[3]), r, 0.5);
-    const double q45 = fma(K_(ex[5]), r, K_(ex[4])), q67 = fma(K_(ex[7]), r, K_(ex[6]));
-    const double q89 = fma(lit::ex9i, r, lit::ex8i), qab = fma(lit::ex11i, r, lit::ex10i);
-    const double q03 = fma(q23, r2, q01), q47 = fma(q67, r2, q45);
-    const double q8c = fma(lit::ex12i, r4, fma(qab, r2, q89));
-    const double p = fma(q8c, r8, fma(q47, r4, q03));
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-}
-#endif
+__shared__ b200e_tabs sh_tab;
 
 enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
 
@@ -348,7 +215,7 @@ __device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long lo
         const real m2 = fmax(s1, s2 * idt0 * idt0) * R_(lit::inv_n);
         real dt1;
         if (m2 <= R_(1e-30)) dt1 = fmax(R_(1e-6), dt0 * R_(1e-3));
-        else dt1 = exp_small(fma(R_(-0.1), log_pos(m2), -K_(ln10_04)));  // 10^(-(2 + log10 dmax)/5)
+        else dt1 = exp_small(sh_tab, fma(R_(-0.1), log_pos(sh_tab, m2), -K_(ln10_04)));  // 10^(-(2 + log10 dmax)/5)
         dt = fmin(fmin(R_(100.0) * dt0, dt1), dtmax);
         nf += 3u;
     }
@@ -358,21 +225,6 @@ __device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long lo
     for (int j = 0; j < N; j++) k1[j] = f0[j];
     le2old = K_(le2_qoldinit);
 }
-
-// min / max of two NON-NEGATIVE reals through their bit patterns (IEEE order == integer order
-// for x >= 0): integer-pipe compares + selects instead of a DSETP on the FP64 pipe plus the
-// NaN-fixup sequence fmin/fmax compile to.  A positive-NaN pattern orders above +inf.
-#if B200E_FP32
-__device__ __forceinline__ float pmin(float a, float b) { return __int_as_float(min(__float_as_int(a), __float_as_int(b))); }
-__device__ __forceinline__ float pmax(float a, float b) { return __int_as_float(max(__float_as_int(a), __float_as_int(b))); }
-#else
-__device__ __forceinline__ double pmin(double a, double b) {
-    return __longlong_as_double(min(__double_as_longlong(a), __double_as_longlong(b)));
-}
-__device__ __forceinline__ double pmax(double a, double b) {
-    return __longlong_as_double(max(__double_as_longlong(a), __double_as_longlong(b)));
-}
-#endif
 
 // One attempted Tsit5 step of the lane's trajectory (perform_step! + stepsize_controller! +
 // step_accept/reject_controller! + the loopheader! checks of the reference's integrator loop).
@@ -384,7 +236,7 @@ struct Lane {
     unsigned nf0, nacc, nrej;  // nf = nf0 (initial-step evaluations) + 6 * (nacc + nrej)
 };
 
-__device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dtmax, const bool clip_dtmax,
+__device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dtmax,
                                            const real abstol, const real reltol, const real snap_tol,
                                            const int maxiters, const real one_plus_eps) {
     real *u = L.u, *k1 = L.k1, *p = L.p;
@@ -452,17 +304,19 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     // ---- PI controller in log space on e2: one log + one exp instead of two pow + sqrt ----
     // accept:  1/q = gamma * qold^b2 / EEst^b1  clamped to [qmin, qmax]
     // reject:  dt *= max(qmin, gamma / EEst^b1)  (< 1, so the same clamp applies)
-    // No special cases: log_pos maps e2 = 0 / subnormal to about -709 and e2 = +inf to +710, for
+    // No special cases: log_pos maps e2 = 0 / subnormal to about -711 and e2 = +inf / NaN to +708, for
     // which the clamps on 1/q decide alone exactly as the reference's (EEst == 0 -> q = 1/qmax;
-    // EEst = Inf -> dt/5), and |b2*le2old - b1*le2| <= 50 stays far inside exp_small's range.
-    const real le2 = log_pos(e2);
+    // EEst = Inf -> dt/5), and |b2*le2old - b1*le2| <= 51 stays far inside exp_small's range.
+    const real le2 = log_pos(sh_tab, e2);
     const real hist = accept ? L.le2old : R_(0.0);
-    real qinv = exp_small(fma(K_(hb2), hist, fma(-K_(hb1), le2, K_(ln_gamma))));  // gamma * e2old^hb2 / e2^hb1
+    real qinv = exp_small(sh_tab, fma(K_(hb2), hist, fma(-K_(hb1), le2, K_(ln_gamma))));  // gamma * e2old^hb2 / e2^hb1
     qinv = pmin(R_(lit::qmax), pmax(K_(qmin), qinv));
     L.dt = dt * qinv;
-    if (clip_dtmax) L.dt = pmin(dtmax, L.dt);  // warp-uniform; only when the caller set dtmax < t1 - t0
+#if B200E_CLIP_DTMAX  // compiled in only when the model sets dtmax < t1 - t0
+    L.dt = pmin(dtmax, L.dt);
+#endif
     if (accept) {
-        L.le2old = fmax(le2, K_(le2_qoldinit));  // qold = max(EEst, 1e-4)
+        L.le2old = le2 > K_(le2_qoldinit) ? le2 : K_(le2_qoldinit);  // qold = max(EEst, 1e-4); le2 is never NaN
         real tn = t + dt;
         if (fabs(tn - t1) < snap_tol) tn = t1;  // fixed_t_for_floatingpoint_error!
         L.t = tn;
@@ -487,13 +341,15 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     double wgt = 1.0;
     Accum A;
     A.init();
+#if !B200E_FP32
+    for (int j = threadIdx.x; j < TAB_N; j += B200E_BLOCK) tab_fill(sh_tab, j);
+    __syncthreads();
+#endif
 
     const real t1 = (real)P.t1, dtmax = (real)P.dtmax;
     const real abstol = (real)P.abstol, reltol = (real)P.reltol;
     const real snap_tol = (real)P.snap_tol;
     const int maxiters = (int)P.maxiters;
-    // the clip to the end point (dt <= t1 - t) already enforces the default dtmax = t1 - t0
-    const bool clip_dtmax = P.dtmax < P.t1 - P.t0;
 #if B200E_FP32
     const real one_plus_eps = R_(1.0) + R_(1.1920928955078125e-07);
 #else
@@ -544,7 +400,7 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
         if (act_m == 0u) continue;
         // ---- step phase: a tight loop, one vote per step, until some lane finishes ----
         do {
-            if (L.state == LANE_ACTIVE) tsit5_step(L, t1, dtmax, clip_dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps);
+            if (L.state == LANE_ACTIVE) tsit5_step(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps);
         } while (__ballot_sync(B200E_FULL, L.state == LANE_ACTIVE) == act_m);
     }
     block_reduce_store<REDUCE>(P, A);

@@ -1,0 +1,201 @@
+// expect_math.cuh -- scalar helpers of the Tsit5 step (third part of the NVRTC translation unit,
+// after the prelude; also compiled for the HOST by tests/test_device_math.py with g++ -mfma so
+// the approximations below are checked against libm on the CPU box).
+//
+// What they serve: the reference's step-size controller evaluates two `pow` and one `sqrt` per
+// attempted step (OrdinaryDiffEq PIController behind src/expectation.jl:191 / :290) and one
+// division per state component in the error norm.  FP64 instruction economy decides this path
+// (ncu, profiles/): a 64-bit literal costs two moves every time it is used, and CUDA's
+// log/exp/div/sqrt each carry a special-case branch.  So
+//   (1) every constant of the step lives in __constant__ memory and is read as a c[bank][off]
+//       operand of the DFMA itself, or is a value whose low 32 bits are zero (a DFMA immediate);
+//   (2) the controller's power function is ONE log and ONE exp, both table-driven: a 128-entry
+//       table in shared memory shrinks the argument so far that a degree-5 / degree-4 polynomial
+//       reaches 1e-15 (9 + 8 FP64 instructions instead of 23 + 22 for the series without tables);
+//   (3) 1/x is MUFU.RCP64H + one cubic Newton step (3 DFMA).
+// Absolute error of log_pos and relative error of exp_small are below 4e-15 on the domain the
+// controller can reach; a relative perturbation d of a step size moves a trajectory by ~5 d * (its
+// global error ~1e-5), and flips an accept/reject or last-step decision with probability ~d per
+// step, so 1e-14 keeps both the 1e-8 parity of sums and the bit-exact counters at 1e9 samples.
+
+#ifndef B200E_EXPECT_MATH_CUH
+#define B200E_EXPECT_MATH_CUH
+
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+#define B200E_MFN __device__ __forceinline__
+#define B200E_CONST __constant__
+#else
+// ---- host twin (tests only) ----
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#define B200E_MFN static inline
+#define B200E_CONST static
+#define __align__(n) __attribute__((aligned(n)))
+static inline int __double2hiint(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+static inline int __double2loint(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b & 0xffffffff); }
+static inline double __hiloint2double(int hi, int lo) {
+    const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double x; std::memcpy(&x, &b, 8); return x;
+}
+#endif
+
+#define R_(x) ((real)(x))
+
+namespace b200e {
+
+namespace lit {
+constexpr double c1 = 0.161, c2 = 0.327, c3 = 0.9, c4 = 0.9800255409045097;
+constexpr double a21 = 0.161;
+constexpr double a31 = -0.008480655492356989, a32 = 0.335480655492357;
+constexpr double a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815;
+constexpr double a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365,
+                 a54 = -0.09249506636175525;
+constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.159367898576159,
+                 a64 = -0.071584973281401, a65 = -0.028269050394068383;
+constexpr double a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996,
+                 a74 = 1.379008574103742, a75 = -3.290069515436081, a76 = 2.324710524099774;
+constexpr double bt1 = -0.00178001105222577714, bt2 = -0.0008164344596567469,
+                 bt3 = 0.007880878010261995, bt4 = -0.1447110071732629, bt5 = 0.5823571654525552,
+                 bt6 = -0.45808210592918697, bt7 = 0.015151515151515152;
+// PI controller on e2 = EEst^2:  EEst^b1 = e2^(b1/2)
+constexpr double hb1 = 0.5 * 7.0 / 50.0, hb2 = 0.5 * 2.0 / 25.0;
+constexpr double gamma = 9.0 / 10.0, qmin = 1.0 / 5.0, qmax = 10.0;
+constexpr double ln_gamma = -0.10536051565782630123;  // log(9/10)
+constexpr double le2_qoldinit = -18.420680743952364;  // log(1e-4^2)
+constexpr double inv_n = 1.0 / B200E_NSTATE;
+constexpr double ln2 = 0.6931471805599453094;
+constexpr double log2e_128 = 128.0 * 1.4426950408889634074, ln2_128 = 0.6931471805599453094 / 128.0;
+constexpr double rnd_magic = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-nearest-integer
+constexpr double two52_1023 = 4503599627370496.0 + 1023.0;
+constexpr double ln10_04 = 0.4 * 2.302585092994045684;
+// series coefficients rounded to the 21 bits a DFMA immediate carries.  Their terms are at most
+// 2^-24 (log: r^3/3, |r| <= 2^-8) resp. 2^-27 (exp: r^3/6, |r| <= 2^-8.5) of the result, so the
+// 2^-21 rounding stays below 2^-45 * 2^-8 ... i.e. under 1e-14 absolute; they cost no register.
+constexpr double third_i = 0x1.55555p-2, fifth_i = 0x1.9999ap-3;
+constexpr double sixth_i = 0x1.55555p-3, r24_i = 0x1.55555p-5;
+}  // namespace lit
+
+#if B200E_FP32
+#define K_(name) ((real)lit::name)
+#else
+struct b200e_consts {
+    double c1, c2, c3, c4, a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, a71,
+        a72, a73, a74, a75, a76, bt1, bt2, bt3, bt4, bt5, bt6, bt7;
+    double hb1, hb2, ln_gamma, qmin, qmax, le2_qoldinit, inv_n;
+    double ln2, log2e_128, ln2_128, ln10_04;
+};
+// not `const`: the compiler must read it from the constant bank instead of folding literals back in
+B200E_CONST b200e_consts KC = {
+    lit::c1, lit::c2, lit::c3, lit::c4, lit::a21, lit::a31, lit::a32, lit::a41, lit::a42, lit::a43, lit::a51,
+    lit::a52, lit::a53, lit::a54, lit::a61, lit::a62, lit::a63, lit::a64, lit::a65, lit::a71, lit::a72, lit::a73,
+    lit::a74, lit::a75, lit::a76, lit::bt1, lit::bt2, lit::bt3, lit::bt4, lit::bt5, lit::bt6, lit::bt7,
+    lit::hb1, lit::hb2, lit::ln_gamma, lit::qmin, lit::qmax, lit::le2_qoldinit, lit::inv_n,
+    lit::ln2, lit::log2e_128, lit::ln2_128, lit::ln10_04};
+#define K_(name) (KC.name)
+#endif
+
+// ---- range-reduction tables (one copy per block in shared memory, filled at kernel start) ----
+constexpr int TAB_BITS = 7, TAB_N = 1 << TAB_BITS;
+struct __align__(16) b200e_lgent { double c, lc; };  // c_j = 1/(1 + (j+1/2)/128),  lc_j = -log c_j
+struct b200e_tabs {
+    b200e_lgent lg[TAB_N];
+    double ex[TAB_N];  // 2^(j/128)
+};
+B200E_MFN void tab_fill(b200e_tabs &T, int j) {
+    const double mid = (j + 0.5) / TAB_N;
+    T.lg[j].c = 1.0 / (1.0 + mid);
+    T.lg[j].lc = log1p(mid);  // = -log(c_j) up to the rounding of the division (1e-16 relative in c)
+    T.ex[j] = exp2((double)j / TAB_N);
+}
+
+// ---- branch-free scalar helpers -----------------------------------------------------------
+#if B200E_FP32
+B200E_MFN float rcp_pos(float b) { return 1.0f / b; }
+B200E_MFN float log_pos(const b200e_tabs &, float x) { return logf(x); }
+B200E_MFN float exp_small(const b200e_tabs &, float y) { return expf(y); }
+B200E_MFN float sqrt_pos(float x) { return sqrtf(x); }
+#else
+// 1/b for normal b > 0: MUFU.RCP64H seed (20 bits: it reads the high word only) + one cubic step
+//   e = 1 - b r;  1/b = r / (1 - e) = r (1 + e + e^2 + O(e^3)),  e^3 <= 2^-60
+B200E_MFN double rcp_pos(double b) {
+    double r;
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+#else
+    r = __hiloint2double(__double2hiint(1.0 / __hiloint2double(__double2hiint(b), 0)), 0);  // same 20-bit class
+#endif
+    double e = fma(-b, r, 1.0);
+    e = fma(e, e, e);
+    return fma(r, e, r);
+}
+// sqrt(x) for normal x > 0: MUFU.RSQ64H seed + two coupled Newton steps (Goldschmidt form)
+B200E_MFN double sqrt_pos(double x) {
+    double y;
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+    y = __hiloint2double(__double2hiint(1.0 / std::sqrt(__hiloint2double(__double2hiint(x), 0))), 0);
+#endif
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, x);
+    return fma(d, h, g);
+}
+// log(x), x > 0:  x = 2^e m, m in [1,2), j = top 7 bits of m's fraction;
+//   log x = e ln2 + lc_j + log1p(r),  r = x * (c_j 2^-e) - 1  (one exact-product DFMA), |r| <= 2^-8,
+//   log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5  (next term 2^-48/6 = 6e-16).
+// c_j 2^-e is formed by subtracting x's exponent field from c_j's.  The high word is clamped so
+// +inf, NaN and sign-bit patterns read as ~2^1023: zero / subnormal x gives about -711 and those
+// about +708, for which the controller's clamps decide alone (EEst = 0 -> q = 1/qmax, EEst = Inf ->
+// dt/5 as in the reference); the result is always finite.
+B200E_MFN double log_pos(const b200e_tabs &T, double x) {
+    unsigned hi = (unsigned)__double2hiint(x);
+    hi = hi < 0x7fdfffffu ? hi : 0x7fdfffffu;
+    const b200e_lgent ent = T.lg[(hi >> (20 - TAB_BITS)) & (TAB_N - 1)];
+    const int chi = __double2hiint(ent.c) - (int)(hi & 0x7ff00000u) + 0x3ff00000;
+    const double r = fma(__hiloint2double((int)hi, __double2loint(x)), __hiloint2double(chi, __double2loint(ent.c)), -1.0);
+    const double ef = __hiloint2double(0x43300000, (int)(hi >> 20)) - lit::two52_1023;  // (double)e, exact
+    const double r2 = r * r;
+    const double a = fma(r, lit::third_i, -0.5), b = fma(r, lit::fifth_i, -0.25);
+    const double q = fma(b, r2, a);
+    return fma(ef, K_(ln2), ent.lc) + fma(q, r2, r);
+}
+// exp(y), |y| < 600:  n = round(128 y / ln2),  exp y = 2^(n >> 7) * 2^((n & 127)/128) * exp(r),
+//   r = y - n ln2/128, |r| <= ln2/256,  exp r - 1 = r + r^2 (1/2 + r/6 + r^2/24)  (next term 1.2e-15)
+B200E_MFN double exp_small(const b200e_tabs &T, double y) {
+    const double t = fma(y, K_(log2e_128), lit::rnd_magic);
+    const int n = __double2loint(t);
+    const double nf = t - lit::rnd_magic;
+    const double r = fma(-nf, K_(ln2_128), y);
+    const double tj = T.ex[n & (TAB_N - 1)];
+    const double r2 = r * r;
+    const double b = fma(fma(r, lit::r24_i, lit::sixth_i), r, 0.5);
+    const double q = fma(b, r2, r);
+    const double p = fma(tj, q, tj);
+    return __hiloint2double(__double2hiint(p) + ((n >> TAB_BITS) << 20), __double2loint(p));
+}
+#endif
+
+// min / max of two NON-NEGATIVE reals through their bit patterns (IEEE order == integer order
+// for x >= 0): integer-pipe compares + selects instead of a DSETP on the FP64 pipe plus the
+// NaN-fixup sequence fmin/fmax compile to.  A positive-NaN pattern orders above +inf.
+#if B200E_FP32
+B200E_MFN float pmin(float a, float b) { return __int_as_float(min(__float_as_int(a), __float_as_int(b))); }
+B200E_MFN float pmax(float a, float b) { return __int_as_float(max(__float_as_int(a), __float_as_int(b))); }
+#elif defined(__CUDACC__) || defined(__CUDACC_RTC__)
+B200E_MFN double pmin(double a, double b) {
+    return __longlong_as_double(min(__double_as_longlong(a), __double_as_longlong(b)));
+}
+B200E_MFN double pmax(double a, double b) {
+    return __longlong_as_double(max(__double_as_longlong(a), __double_as_longlong(b)));
+}
+#endif
+
+}  // namespace b200e
+#endif

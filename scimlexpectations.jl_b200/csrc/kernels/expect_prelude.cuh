@@ -4,6 +4,7 @@
 //   #define B200E_SOLVER   0 Tsit5 | 1 Euler-Maruyama
 //   #define B200E_FP32     0 | 1
 //   #define B200E_BLOCK    threads per block,  B200E_MINBLOCKS  resident blocks per SM
+//   #define B200E_CLIP_DTMAX  1 when the model sets dtmax < t1 - t0
 // and the text of b200e_kparams.h.
 //
 // Dialect of the model source (valid as CUDA device code here and as C in the test oracle):
