@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B200E_ABI_VERSION 1
+#define B200E_ABI_VERSION 2
 
 /* limits (compile-time dims of the generated kernel) */
 #define B200E_MAX_STATE 16
@@ -61,6 +61,14 @@ enum { B200E_FP64 = 0, B200E_FP32 = 1 };
 /* layout of x (and dx): 0 = point-major x[i*nx+j] (what Julia's dim x npts column-major array is),
  *                        1 = SoA x[j*npts+i] */
 enum { B200E_LAYOUT_POINT_MAJOR = 0, B200E_LAYOUT_SOA = 1 };
+/* how points are handed to warps.  DYNAMIC (default): a warp whose lanes run idle takes the next
+ * unassigned points of the launch off a device-side counter, so no warp waits for work another one
+ * still owns (7-18 % faster than STATIC: the SM's warp scheduler does not advance resident warps at
+ * equal pace).  Per-node outputs and all integer counters are identical under both; the floating-point
+ * SUMS of b200e_reduce_samples are accumulated per lane, so under DYNAMIC their last bits depend on the
+ * run-time assignment (differences ~1e-16 relative).  STATIC: lane l owns points l, l+T, l+2T, ...;
+ * sums are bit-reproducible for a given launch shape. */
+enum { B200E_SCHED_DYNAMIC = 0, B200E_SCHED_STATIC = 1 };
 enum { B200E_PDF_NONE = 0, B200E_PDF_UNIFORM = 1, B200E_PDF_NORMAL = 2, B200E_PDF_TRUNCNORMAL = 3 };
 
 /* one factor of GenericDistribution(dists...) (src/distribution_utils.jl:40-48) */
@@ -105,6 +113,8 @@ typedef struct {
     int32_t blocks_per_sm;    /* resident blocks per SM to launch (grid = SMs * this) */
     int32_t refill_threshold; /* lanes of a warp that must be idle before the warp reloads (1..32); 0 = automatic */
     int32_t chunk_points;     /* host-pointer calls are pipelined in chunks of this many points */
+    int32_t schedule;         /* B200E_SCHED_* */
+    int32_t _reserved;
     const char *cache_dir;    /* cubin cache directory, NULL -> $B200E_CACHE_DIR or disabled */
 } b200e_model;
 

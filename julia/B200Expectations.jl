@@ -39,6 +39,7 @@ struct CModel            # b200e_model (field order = include/b200_expect.h)
     pdf::Ptr{PdfDim}
     n_devices::Int32; devices::Ptr{Int32}
     block_size::Int32; blocks_per_sm::Int32; refill_threshold::Int32; chunk_points::Int32
+    schedule::Int32; _reserved::Int32   # 0 dynamic (default), 1 static = bit-reproducible sums
     cache_dir::Cstring
 end
 struct Counters; nf::UInt64; naccept::UInt64; nreject::UInt64; nfail::UInt64; end

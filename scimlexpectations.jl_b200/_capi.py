@@ -17,13 +17,14 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libb200expect.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_STATE, MAX_PARAM, MAX_X, MAX_OUT, MAX_KKL = 16, 32, 32, 16, 32
 OK, ERR_INVALID, ERR_COMPILE, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
 SOLVER_TSIT5, SOLVER_EM = 0, 1
 FP64, FP32 = 0, 1
 LAYOUT_POINT_MAJOR, LAYOUT_SOA = 0, 1
 PDF_NONE, PDF_UNIFORM, PDF_NORMAL, PDF_TRUNCNORMAL = 0, 1, 2, 3
+SCHED_DYNAMIC, SCHED_STATIC = 0, 1
 
 _ERR_NAMES = {ERR_INVALID: "B200E_ERR_INVALID", ERR_COMPILE: "B200E_ERR_COMPILE", ERR_CUDA: "B200E_ERR_CUDA",
               ERR_NO_DEVICE: "B200E_ERR_NO_DEVICE", ERR_NOMEM: "B200E_ERR_NOMEM", ERR_NCCL: "B200E_ERR_NCCL"}
@@ -67,6 +68,7 @@ class Model(C.Structure):
         ("devices", C.POINTER(C.c_int32)),
         ("block_size", C.c_int32), ("blocks_per_sm", C.c_int32),
         ("refill_threshold", C.c_int32), ("chunk_points", C.c_int32),
+        ("schedule", C.c_int32), ("_reserved", C.c_int32),
         ("cache_dir", C.c_char_p),
     ]
 
@@ -182,6 +184,7 @@ class ModelSpec:
     blocks_per_sm: int = 0
     refill_threshold: int = 0
     chunk_points: int = 0
+    schedule: int = 0            # SCHED_DYNAMIC (default) / SCHED_STATIC (bit-reproducible sums)
     cache_dir: Optional[str] = None
 
     def replace(self, **kw) -> "ModelSpec":
@@ -220,6 +223,7 @@ class ModelSpec:
             m.n_devices = len(self.devices)
         m.block_size, m.blocks_per_sm = int(self.block_size), int(self.blocks_per_sm)
         m.refill_threshold, m.chunk_points = int(self.refill_threshold), int(self.chunk_points)
+        m.schedule = int(self.schedule)
         cache = self.cache_dir if self.cache_dir is not None else default_cache_dir()
         if cache:
             cb = cache.encode()

@@ -184,6 +184,7 @@ class EnsembleB200:
     blocks_per_sm: int = 0
     refill_threshold: int = 0
     chunk_points: int = 0
+    schedule: int = 0   # 0 dynamic work distribution (default), 1 static = bit-reproducible sums
 
 
 class SystemMap:
@@ -251,7 +252,8 @@ class ExpectationProblem:
                              u0=list(prob.u0), p=list(prob.p), tspan=tuple(prob.tspan), solver=_capi.SOLVER_EM,
                              n_kkl=S.n, dt_fixed=dt, pdf=self.d.table(), fp_mode=FP32 if ens.fp32 else FP64,
                              devices=ens.devices, block_size=ens.block_size, blocks_per_sm=ens.blocks_per_sm,
-                             refill_threshold=ens.refill_threshold, chunk_points=ens.chunk_points)
+                             refill_threshold=ens.refill_threshold, chunk_points=ens.chunk_points,
+                         schedule=ens.schedule)
         ens = S.ensemblealg
         if not isinstance(ens, EnsembleB200):
             raise TypeError("this package only carries the EnsembleB200 ensemble algorithm (no CPU fallback)")
@@ -265,7 +267,8 @@ class ExpectationProblem:
                          dtmax=float(kw.get("dtmax", 0.0)), maxiters=int(kw.get("maxiters", 100000)),
                          pdf=self.d.table(), fp_mode=FP32 if ens.fp32 else FP64, devices=ens.devices,
                          block_size=ens.block_size, blocks_per_sm=ens.blocks_per_sm,
-                         refill_threshold=ens.refill_threshold, chunk_points=ens.chunk_points)
+                         refill_threshold=ens.refill_threshold, chunk_points=ens.chunk_points,
+                         schedule=ens.schedule)
 
     def handle(self) -> _capi.Handle:
         spec = self.model_spec()

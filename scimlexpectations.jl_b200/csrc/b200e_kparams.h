@@ -23,6 +23,7 @@ struct b200e_kparams {
     double *partials;       // [grid][2*nout] per-block partial sums (reduce mode)
     unsigned long long *cpartials;  // [grid][4] per-block counters
     int *steps;             // optional per-point attempted steps (nodes mode), or null
+    unsigned long long *work_counter;  // dynamic work distribution: next unassigned point of this launch (zeroed by the host)
     const double *kkl_table;  // EM: [nsteps+1][n_kkl] basis values sqrt(2) sin((k-1/2) pi t_n)/((k-1/2) pi)
     long long npts;         // points in this launch
     long long ld;           // SoA leading dimension of x and dx (total points of the caller's array)

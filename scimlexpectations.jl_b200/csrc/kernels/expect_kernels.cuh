@@ -244,7 +244,8 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     // ---- loopheader!: a NaN error estimate in the previous attempt, the iteration cap, or a step
     // below the resolution of t abort the trajectory (dt <= dtmax holds where dt is proposed) ----
     const real dt = pmin(L.dt, t1 - t);  // clip to the end point
-    if (L.failed || (int)(L.nacc + L.nrej) >= maxiters || t + dt == t) {
+    const real tnext = t + dt;
+    if (L.failed || (int)(L.nacc + L.nrej) >= maxiters || same_value(tnext, t)) {
         L.failed = 1;
         L.state = LANE_DONE;
         return;
@@ -278,7 +279,7 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
         tmp[i] = fma(K_(a65), kd5[i],
                      fma(K_(a64), kd4[i], fma(K_(a63), kd3[i], fma(K_(a62), kd2[i], fma(K_(a61), kd1[i], u[i])))));
     }
-    rhs(k, tmp, p, t + dt);
+    rhs(k, tmp, p, tnext);
 #pragma unroll
     for (int i = 0; i < N; i++) {
         kd6[i] = dt * k[i];
@@ -286,7 +287,7 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
                     fma(K_(a75), kd5[i],
                         fma(K_(a74), kd4[i], fma(K_(a73), kd3[i], fma(K_(a72), kd2[i], fma(K_(a71), kd1[i], u[i]))))));
     }
-    rhs(k7, un, p, t + dt);
+    rhs(k7, un, p, tnext);
 
     // ---- embedded error estimate: calculate_residuals + RMS norm, kept squared ----
     real ss = R_(0.0);
@@ -302,7 +303,7 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     }
     // 1/N is a DFMA immediate when N is a power of two
     const real e2 = ss * (((N & (N - 1)) == 0) ? R_(lit::inv_n) : K_(inv_n));  // EEst^2
-    const bool accept = e2 <= one_plus_eps;  // sqrt(e2) <= 1  <=>  e2 <= nextafter(1); false for a NaN
+    const bool accept = le_nonneg(e2, one_plus_eps);  // sqrt(e2) <= 1  <=>  e2 <= nextafter(1); false for a NaN
 
     // ---- PI controller in log space on e2: one log + one exp instead of two pow + sqrt ----
     // accept:  1/q = gamma * qold^b2 / EEst^b1  clamped to [qmin, qmax]
@@ -319,14 +320,14 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     L.dt = pmin(dtmax, L.dt);
 #endif
     if (accept) {
-        L.le2old = le2 > K_(le2_qoldinit) ? le2 : K_(le2_qoldinit);  // qold = max(EEst, 1e-4); le2 is never NaN
-        real tn = t + dt;
-        if (fabs(tn - t1) < snap_tol) tn = t1;  // fixed_t_for_floatingpoint_error!
-        L.t = tn;
+        L.le2old = max_with_negative(le2, R_(lit::le2_qoldinit));  // qold = max(EEst, 1e-4); le2 is never NaN
+        const real left = t1 - tnext;
+        const bool snap = lt_nonneg(abs_bits(left), snap_tol);  // fixed_t_for_floatingpoint_error!
+        L.t = snap ? t1 : tnext;
 #pragma unroll
         for (int i = 0; i < N; i++) { u[i] = un[i]; k1[i] = k7[i]; }
         L.nacc++;
-        if (!(tn < t1)) L.state = LANE_DONE;
+        if (snap || is_negative(left)) L.state = LANE_DONE;  // !(t < t1); left == 0 snaps
     } else {
         // NaN estimate: the reference counts a rejection, dt turns NaN and the solve aborts at the next
         // loop header -- same here through L.failed = 2 (tested on this rarely taken side only)
@@ -337,7 +338,11 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
 
 template <bool REDUCE>
 __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
+#if B200E_DYNAMIC
+    long long next = P.npts;  // the point a lane was handed in the current refill, if any
+#else
     long long next = (long long)blockIdx.x * B200E_BLOCK + threadIdx.x;
+#endif
     long long cur = -1;
 
     Lane L;
@@ -370,9 +375,17 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     int thr_eff = P.refill_threshold > 0 ? P.refill_threshold : 32;
     bool tune = P.refill_threshold <= 0;
 
+#if B200E_DYNAMIC
+    bool more = true;  // warp-uniform: the launch still has unassigned points
+    const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
+#endif
     for (;;) {
         // ---- refill phase: runs only when the set of stepping lanes has changed ----
+#if B200E_DYNAMIC
+        const bool wants = (L.state == LANE_DONE) || (L.state == LANE_EMPTY && more);
+#else
         const bool wants = (L.state == LANE_DONE) || (L.state == LANE_EMPTY && next < P.npts);
+#endif
         const unsigned idle_m = __ballot_sync(B200E_FULL, wants);
         unsigned act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
         if ((idle_m | act_m) == 0u) break;
@@ -386,20 +399,33 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 if (mx * 128u > sm * 5u) thr_eff = 8;  // max > 1.25 * mean
                 tune = false;
             }
-            if (wants) {
-                if (L.state == LANE_DONE) {
-                    emit<REDUCE>(P, cur, L.u, L.p, wgt, A);
-                    if (!REDUCE && P.steps) P.steps[cur] = (int)(L.nacc + L.nrej);
-                    A.count(L.nf0 + 6u * (L.nacc + L.nrej), L.nacc, L.nrej, L.failed ? 1u : 0u);
-                    L.state = LANE_EMPTY;
-                }
-                if (next < P.npts) {
-                    cur = next;
-                    next += (long long)gridDim.x * B200E_BLOCK;
-                    L.nf0 = 0; L.nacc = 0; L.nrej = 0; L.failed = 0;
-                    start_trajectory(P, cur, L.u, L.p, L.k1, L.t, L.dt, L.le2old, wgt, L.nf0);
-                    L.state = (L.t < t1) ? LANE_ACTIVE : LANE_DONE;
-                }
+            if (L.state == LANE_DONE) {
+                emit<REDUCE>(P, cur, L.u, L.p, wgt, A);
+                if (!REDUCE && P.steps) P.steps[cur] = (int)(L.nacc + L.nrej);
+                A.count(L.nf0 + 6u * (L.nacc + L.nrej), L.nacc, L.nrej, L.failed ? 1u : 0u);
+                L.state = LANE_EMPTY;
+            }
+#if B200E_DYNAMIC
+            // the warp takes the next popc(idle) points of the launch off a global counter: which warp
+            // solves which point is decided at run time, so a warp the scheduler favoured simply takes more
+            if (more) {
+                unsigned long long base = 0ull;
+                if ((threadIdx.x & 31) == 0) base = atomicAdd(P.work_counter, (unsigned long long)__popc(idle_m));
+                base = __shfl_sync(B200E_FULL, base, 0);
+                next = wants ? (long long)base + __popc(idle_m & lt_mask) : P.npts;
+                more = (long long)base + __popc(idle_m) < P.npts;
+            }
+            if (wants && next < P.npts) {
+                cur = next;
+                next = P.npts;
+#else
+            if (wants && next < P.npts) {
+                cur = next;
+                next += (long long)gridDim.x * B200E_BLOCK;
+#endif
+                L.nf0 = 0; L.nacc = 0; L.nrej = 0; L.failed = 0;
+                start_trajectory(P, cur, L.u, L.p, L.k1, L.t, L.dt, L.le2old, wgt, L.nf0);
+                L.state = (L.t < t1) ? LANE_ACTIVE : LANE_DONE;
             }
             act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
         }
@@ -437,7 +463,19 @@ __device__ __forceinline__ void em_run(const b200e_kparams &P) {
     A.init();
     const long long nsteps = P.em_nsteps;
     const real t0 = (real)P.t0, t1 = (real)P.t1, h = (real)P.dt_fixed;
+#if B200E_DYNAMIC
+    // every lane takes the same number of steps, but resident warps do not advance at equal pace:
+    // a warp takes the next 32 points off the launch's counter instead of owning a fixed stride
+    for (;;) {
+        unsigned long long base = 0ull;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(P.work_counter, 32ull);
+        base = __shfl_sync(B200E_FULL, base, 0);
+        if ((long long)base >= P.npts) break;
+        const long long i = (long long)base + (threadIdx.x & 31);
+        if (i >= P.npts) continue;  // ragged last chunk: the next grab ends the loop for the whole warp
+#else
     for (long long i = (long long)blockIdx.x * B200E_BLOCK + threadIdx.x; i < P.npts; i += T) {
+#endif
         double xs[NX];
         load_point(P, i, xs);
         const double wgt = P.weight_by_pdf ? pdf_weight(P, xs) : 1.0;

@@ -187,21 +187,43 @@ B200E_MFN double exp_small(const b200e_tabs &T, double y) {
 // min / max of two NON-NEGATIVE reals through their bit patterns (IEEE order == integer order
 // for x >= 0): integer-pipe compares + selects instead of a DSETP on the FP64 pipe plus the
 // NaN-fixup sequence fmin/fmax compile to.  A positive-NaN pattern orders above +inf.
-// |x| through the sign bit (an ALU LOP3; fabs of a double is a DADD on the FP64 pipe)
+// ---- comparisons on the integer pipe --------------------------------------------------------
+// A DSETP occupies the FP64 pipe for 2 cycles; integer compares on the bit patterns ride along for
+// free (profiles/r1_dp_operands_ubench.txt).  IEEE order equals integer order for non-negative
+// values, NaN patterns order above +inf, and for two NEGATIVE values the order is reversed.
 #if B200E_FP32
 B200E_MFN float abs_bits(float x) { return fabsf(x); }
-#else
-B200E_MFN double abs_bits(double x) { return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x)); }
-#endif
-#if B200E_FP32
 B200E_MFN float pmin(float a, float b) { return __int_as_float(min(__float_as_int(a), __float_as_int(b))); }
 B200E_MFN float pmax(float a, float b) { return __int_as_float(max(__float_as_int(a), __float_as_int(b))); }
+B200E_MFN bool same_value(float a, float b) { return a == b; }
+B200E_MFN bool le_nonneg(float a, float b) { return a <= b; }
+B200E_MFN bool lt_nonneg(float a, float b) { return a < b; }
+B200E_MFN bool is_negative(float a) { return a < 0.0f; }
+B200E_MFN float max_with_negative(float a, float q) { return fmaxf(a, q); }
 #elif defined(__CUDACC__) || defined(__CUDACC_RTC__)
+// |x| through the sign bit (an ALU LOP3; fabs of a double is a DADD on the FP64 pipe)
+B200E_MFN double abs_bits(double x) { return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x)); }
 B200E_MFN double pmin(double a, double b) {
     return __longlong_as_double(min(__double_as_longlong(a), __double_as_longlong(b)));
 }
 B200E_MFN double pmax(double a, double b) {
     return __longlong_as_double(max(__double_as_longlong(a), __double_as_longlong(b)));
+}
+// a == b for finite values of equal sign of zero (used for t + dt == t)
+B200E_MFN bool same_value(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
+// a <= b / a < b for a >= 0 or NaN (false for every NaN pattern), b >= 0 finite
+B200E_MFN bool le_nonneg(double a, double b) {
+    return (unsigned long long)__double_as_longlong(a) <= (unsigned long long)__double_as_longlong(b);
+}
+B200E_MFN bool lt_nonneg(double a, double b) {
+    return (unsigned long long)__double_as_longlong(a) < (unsigned long long)__double_as_longlong(b);
+}
+B200E_MFN bool is_negative(double a) { return __double2hiint(a) < 0; }  // sign bit (true for -0.0)
+// max(a, q) for finite a and a NEGATIVE constant q: a >= 0 has the smaller unsigned pattern (no sign
+// bit), and of two negative values the smaller pattern is the smaller magnitude, i.e. the larger value
+B200E_MFN double max_with_negative(double a, double q) {
+    return __longlong_as_double((long long)min((unsigned long long)__double_as_longlong(a),
+                                               (unsigned long long)__double_as_longlong(q)));
 }
 #endif
 

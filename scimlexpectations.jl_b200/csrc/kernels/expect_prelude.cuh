@@ -11,6 +11,10 @@
 //   `real` scalars, B200E_FN linkage, B200E_REAL(1.5) literals, math via sin/cos/exp/log/sqrt/
 //   fabs/pow/fmin/fmax (CUDA resolves the float overloads in FP32 mode).
 
+#ifndef B200E_DYNAMIC
+#define B200E_DYNAMIC 0
+#endif
+
 #if B200E_FP32
 typedef float real;
 #define B200E_REAL(x) x##f

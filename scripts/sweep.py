@@ -14,8 +14,10 @@ if len(sys.argv) > 3:
 for name in models:
     X = sample_points(name, N, seed=2)
     ref = None
-    for blk, per, refill in configs:
-        spec = sme.models.builtin(name, block_size=blk, blocks_per_sm=per, refill_threshold=refill)
+    for cfg in configs:
+        blk, per, refill = cfg[:3]
+        sched = cfg[3] if len(cfg) > 3 else 0
+        spec = sme.models.builtin(name, block_size=blk, blocks_per_sm=per, refill_threshold=refill, schedule=sched)
         try:
             with sme.Handle(spec) as h:
                 d = h.device_array(X.shape).upload(X)
@@ -27,8 +29,8 @@ for name in models:
                 d.free()
                 if ref is None:
                     ref = (s, c)
-                ok = c == ref[1] and np.allclose(s, ref[0], rtol=1e-12)
-                print(json.dumps({"model": name, "block": blk, "per_sm": per, "refill": refill, "kernel_ms": round(best, 4),
+                ok = c == ref[1] and np.allclose(s, ref[0], rtol=1e-11)
+                print(json.dumps({"model": name, "block": blk, "per_sm": per, "refill": refill, "sched": sched, "kernel_ms": round(best, 4),
                                   "evals_per_s": round(N / best * 1e3 / 1e9, 3), "regs": st["regs_per_thread"], "grid": st["grid"],
                                   "occ": st["blocks_per_sm_occ"], "local": st["local_bytes_per_thread"], "same": bool(ok)}), flush=True)
         except Exception as e:
