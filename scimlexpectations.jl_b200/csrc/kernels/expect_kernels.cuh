@@ -336,13 +336,17 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     }
 }
 
-template <bool REDUCE>
+template <bool REDUCE, bool DYN>
 __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
-#if B200E_DYNAMIC
-    long long next = P.npts;  // the point a lane was handed in the current refill, if any
-#else
-    long long next = (long long)blockIdx.x * B200E_BLOCK + threadIdx.x;
-#endif
+    // Work distribution.  Static: lane l owns points l, l+T, l+2T, ... (T = grid * block).  Dynamic:
+    // whenever a warp refills, its idle lanes take the next consecutive points off the launch's counter;
+    // which warp solves which point is decided at run time, so a warp the SM favoured simply takes more (resident warps do not advance at equal pace, and with fixed
+    // ownership the last ones finish alone, latency-bound).  A launch with at most one point per lane
+    // has nothing to balance: the host launches the static instantiation for those (no atomics in the
+    // small Koopman refinement rounds) and whenever the model asks for B200E_SCHED_STATIC.
+    const long long T = (long long)gridDim.x * B200E_BLOCK;
+    constexpr bool dyn = DYN;
+    long long next = dyn ? P.npts : (long long)blockIdx.x * B200E_BLOCK + threadIdx.x;
     long long cur = -1;
 
     Lane L;
@@ -375,17 +379,12 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     int thr_eff = P.refill_threshold > 0 ? P.refill_threshold : 32;
     bool tune = P.refill_threshold <= 0;
 
-#if B200E_DYNAMIC
-    bool more = true;  // warp-uniform: the launch still has unassigned points
+    bool more = dyn;  // dynamic mode, warp-uniform: the launch still has unassigned points
     const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
-#endif
     for (;;) {
         // ---- refill phase: runs only when the set of stepping lanes has changed ----
-#if B200E_DYNAMIC
-        const bool wants = (L.state == LANE_DONE) || (L.state == LANE_EMPTY && more);
-#else
-        const bool wants = (L.state == LANE_DONE) || (L.state == LANE_EMPTY && next < P.npts);
-#endif
+        const bool wants = (L.state == LANE_DONE) ||
+                           (L.state == LANE_EMPTY && (dyn ? more : next < P.npts));
         const unsigned idle_m = __ballot_sync(B200E_FULL, wants);
         unsigned act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
         if ((idle_m | act_m) == 0u) break;
@@ -405,24 +404,19 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 A.count(L.nf0 + 6u * (L.nacc + L.nrej), L.nacc, L.nrej, L.failed ? 1u : 0u);
                 L.state = LANE_EMPTY;
             }
-#if B200E_DYNAMIC
-            // the warp takes the next popc(idle) points of the launch off a global counter: which warp
-            // solves which point is decided at run time, so a warp the scheduler favoured simply takes more
-            if (more) {
-                unsigned long long base = 0ull;
-                if ((threadIdx.x & 31) == 0) base = atomicAdd(P.work_counter, (unsigned long long)__popc(idle_m));
-                base = __shfl_sync(B200E_FULL, base, 0);
-                next = wants ? (long long)base + __popc(idle_m & lt_mask) : P.npts;
-                more = (long long)base + __popc(idle_m) < P.npts;
+            if (dyn) {
+                next = P.npts;
+                if (more) {  // one atomic per refill: the warp takes the next popc(idle) points of the launch
+                    unsigned long long base = 0ull;
+                    if ((threadIdx.x & 31) == 0) base = atomicAdd(P.work_counter, (unsigned long long)__popc(idle_m));
+                    base = __shfl_sync(B200E_FULL, base, 0);
+                    if (wants) next = (long long)base + __popc(idle_m & lt_mask);
+                    more = (long long)base + __popc(idle_m) < P.npts;
+                }
             }
             if (wants && next < P.npts) {
                 cur = next;
-                next = P.npts;
-#else
-            if (wants && next < P.npts) {
-                cur = next;
-                next += (long long)gridDim.x * B200E_BLOCK;
-#endif
+                next = dyn ? P.npts : next + T;
                 L.nf0 = 0; L.nacc = 0; L.nrej = 0; L.failed = 0;
                 start_trajectory(P, cur, L.u, L.p, L.k1, L.t, L.dt, L.le2old, wgt, L.nf0);
                 L.state = (L.t < t1) ? LANE_ACTIVE : LANE_DONE;
@@ -440,12 +434,22 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
 
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_nodes(const __grid_constant__ b200e_kparams P) {
-    tsit5_run<false>(P);
+    tsit5_run<false, false>(P);
 }
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_reduce(const __grid_constant__ b200e_kparams P) {
-    tsit5_run<true>(P);
+    tsit5_run<true, false>(P);
 }
+#if B200E_DYNAMIC
+extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
+b200e_nodes_dyn(const __grid_constant__ b200e_kparams P) {
+    tsit5_run<false, true>(P);
+}
+extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
+b200e_reduce_dyn(const __grid_constant__ b200e_kparams P) {
+    tsit5_run<true, true>(P);
+}
+#endif
 
 #else
 // ------------------------------------------------------------------------------------------
@@ -456,26 +460,28 @@ b200e_reduce(const __grid_constant__ b200e_kparams P) {
 // ------------------------------------------------------------------------------------------
 constexpr int NK = B200E_NKKL;
 
-template <bool REDUCE>
+template <bool REDUCE, bool DYN>
 __device__ __forceinline__ void em_run(const b200e_kparams &P) {
     const long long T = (long long)gridDim.x * B200E_BLOCK;
     Accum A;
     A.init();
     const long long nsteps = P.em_nsteps;
     const real t0 = (real)P.t0, t1 = (real)P.t1, h = (real)P.dt_fixed;
-#if B200E_DYNAMIC
-    // every lane takes the same number of steps, but resident warps do not advance at equal pace:
-    // a warp takes the next 32 points off the launch's counter instead of owning a fixed stride
-    for (;;) {
-        unsigned long long base = 0ull;
-        if ((threadIdx.x & 31) == 0) base = atomicAdd(P.work_counter, 32ull);
-        base = __shfl_sync(B200E_FULL, base, 0);
-        if ((long long)base >= P.npts) break;
-        const long long i = (long long)base + (threadIdx.x & 31);
-        if (i >= P.npts) continue;  // ragged last chunk: the next grab ends the loop for the whole warp
-#else
-    for (long long i = (long long)blockIdx.x * B200E_BLOCK + threadIdx.x; i < P.npts; i += T) {
-#endif
+    // every lane takes the same number of steps, but resident warps do not advance at equal pace: in
+    // dynamic mode a warp takes the next 32 points off the launch's counter instead of owning a fixed
+    // stride (the host launches the static instantiation when there is at most one point per lane)
+    constexpr bool dyn = DYN;
+    for (long long i = (long long)blockIdx.x * B200E_BLOCK + threadIdx.x;; i += T) {
+        if (dyn) {
+            unsigned long long base = 0ull;
+            if ((threadIdx.x & 31) == 0) base = atomicAdd(P.work_counter, 32ull);
+            base = __shfl_sync(B200E_FULL, base, 0);
+            if ((long long)base >= P.npts) break;
+            i = (long long)base + (threadIdx.x & 31);
+            if (i >= P.npts) continue;  // ragged last pool: the next grab ends the loop for the whole warp
+        } else if (i >= P.npts) {
+            break;
+        }
         double xs[NX];
         load_point(P, i, xs);
         const double wgt = P.weight_by_pdf ? pdf_weight(P, xs) : 1.0;
@@ -523,12 +529,22 @@ __device__ __forceinline__ void em_run(const b200e_kparams &P) {
 
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_nodes(const __grid_constant__ b200e_kparams P) {
-    em_run<false>(P);
+    em_run<false, false>(P);
 }
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_reduce(const __grid_constant__ b200e_kparams P) {
-    em_run<true>(P);
+    em_run<true, false>(P);
 }
+#if B200E_DYNAMIC
+extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
+b200e_nodes_dyn(const __grid_constant__ b200e_kparams P) {
+    em_run<false, true>(P);
+}
+extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
+b200e_reduce_dyn(const __grid_constant__ b200e_kparams P) {
+    em_run<true, true>(P);
+}
+#endif
 #endif
 
 }  // namespace b200e

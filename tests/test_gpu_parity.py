@@ -148,13 +148,18 @@ def test_static_schedule_is_bit_reproducible_and_dynamic_agrees(gpu):
     for name in ("lotka_volterra", "oscillator_noise"):
         n = _n(name, 100003)
         x = sample_points(name, n, seed=11)
-        with gpu.Handle(gpu.models.builtin(name, schedule=1)) as h:
+        # a small launch shape so that the batch holds several points per lane (launches with at most
+        # one point per lane have nothing to balance and run statically under either schedule)
+        shape = dict(block_size=32, blocks_per_sm=1)
+        with gpu.Handle(gpu.models.builtin(name, schedule=1, **shape)) as h:
+            assert h.last_stats is not None
             s_a, q_a, c_a = h.reduce_samples(x)
             s_b, q_b, c_b = h.reduce_samples(x)
             nodes_static, steps_static = h.eval_nodes(x, want_steps=True)
         assert np.array_equal(s_a, s_b) and np.array_equal(q_a, q_b) and c_a == c_b
-        with gpu.Handle(gpu.models.builtin(name)) as h:
+        with gpu.Handle(gpu.models.builtin(name, **shape)) as h:
             s_d, q_d, c_d = h.reduce_samples(x)
+            assert h.last_stats()["grid"] * 32 < n
             nodes_dyn, steps_dyn = h.eval_nodes(x, want_steps=True)
         assert c_d == c_a
         assert np.array_equal(nodes_dyn, nodes_static) and np.array_equal(steps_dyn, steps_static)
