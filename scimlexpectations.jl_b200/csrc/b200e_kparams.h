@@ -23,7 +23,11 @@ struct b200e_kparams {
     double *partials;       // [grid][2*nout] per-block partial sums (reduce mode)
     unsigned long long *cpartials;  // [grid][4] per-block counters
     int *steps;             // optional per-point attempted steps (nodes mode), or null
-    unsigned long long *work_counter;  // dynamic work distribution: next unassigned point of this launch (zeroed by the host)
+    unsigned long long *work_counter;  // [0] next unassigned point of this launch (dynamic work distribution),
+                                       // [1] blocks that have stored their partials; both are zero between
+                                       // launches: the last block to finish resets them
+    double *final_sums;                // optional [2*nout]: the last block folds all per-block partials of the launch
+    unsigned long long *final_counts;  // optional [4]: same for the counters
     const double *kkl_table;  // EM: [nsteps+1][n_kkl] basis values sqrt(2) sin((k-1/2) pi t_n)/((k-1/2) pi)
     long long npts;         // points in this launch
     long long ld;           // SoA leading dimension of x and dx (total points of the caller's array)

@@ -146,6 +146,43 @@ __device__ __forceinline__ void block_reduce_store(const b200e_kparams &P, Accum
         for (int w = 0; w < NWARPS; w++) t += scnt[w][k];
         P.cpartials[(long long)blockIdx.x * 4 + k] = t;
     }
+    // ---- the last block to get here folds the partials of the whole launch (fixed order: the result
+    // depends on the launch shape only) and re-arms the launch's counters, so a single-launch call needs
+    // no finalize kernels and no memset ----
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(P.work_counter + 1, 1ull) == (unsigned long long)(gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) { P.work_counter[0] = 0ull; P.work_counter[1] = 0ull; }
+    // one warp per column (lane-strided compensated sum, then the shuffle tree): no block barriers
+    const long long rows = gridDim.x;
+    const int nsum = (REDUCE && P.final_sums) ? NACC : 0;
+    const int ncol = nsum + (P.final_counts ? 4 : 0);
+    for (int c = warp; c < ncol; c += NWARPS) {
+        if (c < nsum) {
+            double s = 0.0, comp = 0.0;  // Neumaier
+            for (long long r = lane; r < rows; r += 32) {
+                const double v = __ldcg(P.partials + r * NACC + c);
+                const double t = s + v;
+                comp += (fabs(s) >= fabs(v)) ? ((s - t) + v) : ((v - t) + s);
+                s = t;
+            }
+            s += comp;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(B200E_FULL, s, off);
+            if (lane == 0) P.final_sums[c] = s;
+        } else {
+            const int k = c - nsum;
+            unsigned long long s = 0ull;
+            for (long long r = lane; r < rows; r += 32) s += __ldcg(P.cpartials + r * 4 + k);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(B200E_FULL, s, off);
+            if (lane == 0) P.final_counts[k] = s;
+        }
+    }
 }
 
 #if B200E_SOLVER == 0
