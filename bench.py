@@ -284,6 +284,19 @@ def run_b200(args):
             torch.cuda.synchronize()
         return s, s2, c, st
 
+    def step_generated():
+        # solve(exprob, MonteCarlo(n)) as the user calls it: rand(d) is drawn inside the kernel from the
+        # counter-based stream (seed, index); rank r owns indices [r*n, (r+1)*n)
+        s, s2, c = h.reduce_generated(args.seed, n, first_index=rank * n)
+        st = h.last_stats()
+        if world > 1:
+            red[:nout] = torch.from_numpy(s)
+            red[nout:2 * nout] = torch.from_numpy(s2)
+            red[2 * nout:] = torch.tensor([c["nf"], c["naccept"], c["nreject"], c["nfail"]], dtype=torch.float64)
+            dist.all_reduce(red)
+            torch.cuda.synchronize()
+        return s, s2, c, st
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -315,6 +328,7 @@ def run_b200(args):
     clocks = sampler.stop()
     Te, _, e_total_ms, _, (se, s2e, ce, ste) = timed(step_e2e, max(3, args.steps // 4), 3)
     e_steps = max(3, args.steps // 4)
+    Tg, g_kernel_ms, _, _, (sg, s2g, cg, stg) = timed(step_generated, args.steps, 3)
 
     value = world * n * args.steps / T
     e2e_value = world * n * e_steps / Te
@@ -345,6 +359,14 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(ste["h2d_bytes"]),
                     "d2h_bytes_per_step": int(ste["d2h_bytes"]), "ms_per_step": Te / e_steps * 1e3,
                     "api": "b200e_reduce_samples(host pinned x) -> host sums"},
+            # not the contract's e2e (its inputs never exist on the host): the public MonteCarlo call with the
+            # sampler inside the kernel, the configuration a user of solve(exprob, MonteCarlo(n)) runs
+            "e2e_device_sampling": {"value": world * n * args.steps / Tg, "unit": "evals/s", "h2d_bytes_per_step": 0,
+                                    "d2h_bytes_per_step": int(stg["d2h_bytes"]), "ms_per_step": Tg / args.steps * 1e3,
+                                    "kernel_ms": float(np.mean(g_kernel_ms)),
+                                    "expectation": (sg / n).tolist(),
+                                    "api": "b200e_reduce_generated(seed, first_index, n) -> host sums "
+                                           "(Philox4x32-10 stream drawn in registers; b200e_sample_host reproduces it bit for bit)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64" if not args.fp32 else "fp32", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,

@@ -182,6 +182,24 @@ int b200e_device_free(b200e_handle *h, void *dptr);
 int b200e_memcpy_h2d(b200e_handle *h, void *dptr, const void *src, int64_t bytes);
 int b200e_memcpy_d2h(b200e_handle *h, void *dst, const void *dptr, int64_t bytes);
 
+/* ---- MonteCarlo with device-side sampling --------------------------------------
+ * Replaces `rand(d)` inside prob_func of solve(exprob, MonteCarlo(n)) (src/expectation.jl:277-280, :304-305;
+ * src/distribution_utils.jl:43).  Sample i of stream `seed` is a pure function of (seed, i): Philox4x32-10
+ * -> 52-bit uniforms -> inverse CDF of each factor of the model's product density, written with exactly
+ * rounded operations only (csrc/kernels/expect_sampling.cuh), so the three entry points below produce
+ * bit-identical doubles on the host and on the device. */
+
+/* sum / sumsq / counters over samples first_index .. first_index + n - 1 of stream `seed`, drawn inside
+ * the kernel (weight 1, as MonteCarlo): nothing but the 2*nout + 4 results crosses PCIe. */
+int b200e_reduce_generated(b200e_handle *h, uint64_t seed, uint64_t first_index, int64_t n, double *sum,
+                           double *sumsq, b200e_counters *c);
+/* the host twin: the same samples into caller memory, for the CPU arm and for tests.  Takes the model, not a
+ * handle: it needs no device (errors go to b200e_last_error(NULL)). */
+int b200e_sample_host(const b200e_model *model, uint64_t seed, uint64_t first_index, int64_t n, int32_t layout,
+                      double *x);
+/* the same samples written by the device (x: host or device pointer) */
+int b200e_sample_device(b200e_handle *h, uint64_t seed, uint64_t first_index, int64_t n, int32_t layout, double *x);
+
 /* ---- the caller above the path, moved next to it (optional fast path for Koopman) ---------------- */
 typedef struct {
     double reltol, abstol; /* ireltol / iabstol of solve(exprob, Koopman(); ...) */

@@ -4,7 +4,7 @@ The directory name contains a dot, so import it through the alias module at the 
 ``import scimlexpectations_jl_b200 as sme``.
 """
 from . import _capi, api, cubature, models  # noqa: F401
-from ._capi import (B200Error, DeviceArray, Handle, ModelSpec, PinnedArray, compile_check, device_count,  # noqa: F401
+from ._capi import (B200Error, DeviceArray, Handle, ModelSpec, PinnedArray, compile_check, device_count, sample_host,  # noqa: F401
                     load_library, measure_fma_peak)
 from .api import (EM, B200Cubature, BatchIntegralFunction, CubatureJLh, EnsembleB200, ExpectationProblem,  # noqa: F401
                   ExpectationSolution, GenericDistribution, Koopman, MonteCarlo, Normal, ODEProblem,

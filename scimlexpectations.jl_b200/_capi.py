@@ -36,6 +36,7 @@ EXPORTS = [
     "b200e_last_stats", "b200e_set_steps_buffer", "b200e_host_alloc", "b200e_host_free",
     "b200e_device_alloc", "b200e_device_free", "b200e_memcpy_h2d", "b200e_memcpy_d2h",
     "b200e_measure_fma_peak", "b200e_device_count", "b200e_eval_regions", "b200e_koopman_solve",
+    "b200e_reduce_generated", "b200e_sample_host", "b200e_sample_device",
 ]
 
 
@@ -141,6 +142,9 @@ def load_library():
     L.b200e_eval_regions.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200e_koopman_solve.argtypes = [H, C.c_void_p, C.c_void_p, C.POINTER(CubatureOpts), C.c_void_p, C.c_void_p,
                                       C.POINTER(CubatureStats)]
+    L.b200e_reduce_generated.argtypes = [H, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(Counters)]
+    L.b200e_sample_host.argtypes = [C.POINTER(Model), C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_void_p]
+    L.b200e_sample_device.argtypes = [H, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_void_p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("b200e_abi_version", "b200e_device_count"):
@@ -149,6 +153,19 @@ def load_library():
         raise ImportError(f"libb200expect ABI {L.b200e_abi_version()} != binding ABI {ABI_VERSION}")
     _lib = L
     return L
+
+
+def sample_host(spec: "ModelSpec", seed: int, n: int, *, first_index: int = 0, layout=LAYOUT_POINT_MAJOR):
+    """``b200e_sample_host``: samples ``first_index .. first_index+n-1`` of stream ``seed`` of the model's
+    product density, bit-identical to what the kernels draw.  Needs no GPU."""
+    L = load_library()
+    m, keep = spec.to_c()
+    x = np.empty((n, spec.nx) if layout == LAYOUT_POINT_MAJOR else (spec.nx, n), dtype=np.float64)
+    rc = L.b200e_sample_host(C.byref(m), int(seed), int(first_index), int(n), int(layout), x.ctypes.data)
+    del keep
+    if rc != OK:
+        raise B200Error(rc, _tls_error())
+    return x
 
 
 def device_count() -> int:
@@ -465,6 +482,31 @@ class Handle:
         self._check(self.L.b200e_eval_regions(self._h, c.ctypes.data, w.ctypes.data, n, val.ctypes.data,
                                               err.ctypes.data, split.ctypes.data))
         return val, err, split
+
+    def reduce_generated(self, seed: int, n: int, *, first_index: int = 0):
+        """``solve(exprob, MonteCarlo(n))`` with ``rand(d)`` drawn inside the kernel (reference
+        src/expectation.jl:277-293): samples ``first_index .. first_index+n-1`` of stream ``seed``.
+        Returns ``(sum, sumsq, counters)``; ``sample_host`` yields the identical points for a CPU arm."""
+        s = np.zeros(self.spec.nout)
+        s2 = np.zeros(self.spec.nout)
+        c = Counters()
+        self._check(self.L.b200e_reduce_generated(self._h, int(seed), int(first_index), int(n), s.ctypes.data,
+                                                  s2.ctypes.data, C.byref(c)))
+        return s, s2, c.as_dict()
+
+    def sample_host(self, seed: int, n: int, *, first_index: int = 0, layout=LAYOUT_POINT_MAJOR):
+        """Host twin of the in-kernel sampler: bit-identical to what ``reduce_generated`` draws."""
+        return sample_host(self.spec, seed, n, first_index=first_index, layout=layout)
+
+    def sample_device(self, seed: int, n: int, *, first_index: int = 0, layout=LAYOUT_POINT_MAJOR, out=None):
+        """The same samples written by the device (into ``out``: a DeviceArray, or a new host array)."""
+        nx = self.spec.nx
+        if out is None:
+            out = np.empty((n, nx) if layout == LAYOUT_POINT_MAJOR else (nx, n), dtype=np.float64)
+        op, ok = _as_pointer(out, None)
+        self._check(self.L.b200e_sample_device(self._h, int(seed), int(first_index), int(n), int(layout), op))
+        del ok
+        return out
 
     def koopman_solve(self, lb, ub, *, reltol=1e-2, abstol=1e-2, maxevals=1000000):
         """``solve(exprob, Koopman(); quadalg=CubatureJLh(), batch=...)`` as ONE C call: hcubature_v's region

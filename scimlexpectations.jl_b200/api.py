@@ -306,13 +306,18 @@ class Koopman:
 
 @dataclass
 class MonteCarlo:
-    """``MonteCarlo(trajectories)``.  ``seed`` keys the host-generated sample stream (block b is a
-    pure function of (seed, b)); ``samples`` supplies a caller-generated set instead -- the "same
-    host-generated sample set" the CPU arm consumes."""
+    """``MonteCarlo(trajectories)``.  The reference draws ``rand(d)`` inside ``prob_func`` for every
+    trajectory (expectation.jl:278); here ``seed`` keys a counter-based stream (sample i is a pure
+    function of (seed, i)) that the kernel draws in registers (``sampler="device"``, the default:
+    nothing crosses PCIe) and ``sample_host`` reproduces bit for bit for a CPU arm.
+    ``sampler="host"`` generates the numpy PCG64 block stream on the host instead (block b is a pure
+    function of (seed, b)) and ships it; ``samples`` supplies a caller-generated set -- the "same
+    host-generated sample set" both arms consume."""
     trajectories: int
     seed: int = 0
     samples: Any = None
     block: int = 1 << 20
+    sampler: str = "device"
 
 
 @dataclass(frozen=True)
@@ -409,6 +414,12 @@ def _solve_montecarlo(prob: ExpectationProblem, alg: MonteCarlo):
         s, _, c = h.reduce_samples(alg.samples, weight_by_pdf=False, npts=n)
         total += s
         counters = c
+    elif alg.sampler == "device":
+        s, _, c = h.reduce_generated(alg.seed, n)
+        total += s
+        counters = c
+    elif alg.sampler != "host":
+        raise ValueError(f"unknown sampler {alg.sampler!r} (device | host)")
     else:
         done, b = 0, 0
         while done < n:

@@ -11,8 +11,11 @@
 // device form of one factor of the product density: logpdf(x) = logc - 0.5*((x-mu)*inv_sigma)^2
 // inside [lo,hi], -inf outside.  logc folds -log(sigma) - log(2pi)/2 - log(cdf(hi)-cdf(lo))
 // (or -log(hi-lo) for uniform, where inv_sigma = 0) and is computed once on the host.
+// smp_*: constants of the counter-based sampler (kernels/expect_sampling.cuh): uniform (lo, hi-lo, -, -),
+// normal / truncated normal (mu, sigma, cdf(lo), cdf(hi) - cdf(lo)).
 struct b200e_kpdf {
     double lo, hi, mu, inv_sigma, logc;
+    double smp_a, smp_b, smp_c, smp_d;
     int kind;
     int _pad;
 };
@@ -40,6 +43,10 @@ struct b200e_kparams {
     int weight_by_pdf;
     int refill_threshold;
     int want_sumsq;
+    int gen;                // 1: points are drawn in the kernel (sample gen_first + i of stream gen_seed), x is unused
+    int _pad0;
+    unsigned long long gen_seed;
+    long long gen_first;
     double u0_nom[B200E_KP_MAX_STATE];
     double p_nom[B200E_KP_MAX_PARAM];
     b200e_kpdf pdf[B200E_KP_MAX_X];

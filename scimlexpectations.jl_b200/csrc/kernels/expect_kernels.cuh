@@ -48,8 +48,14 @@ __device__ __forceinline__ double pdf_weight(const b200e_kparams &P, const doubl
     return exp(s);
 }
 
+// GEN: the point is not loaded but drawn -- rand(d) of the MonteCarlo prob_func (expectation.jl:278) --
+// from the counter-based stream, in registers (a separate instantiation: the sampler's code and
+// registers stay out of the kernels that read x)
+template <bool GEN>
 __device__ __forceinline__ void load_point(const b200e_kparams &P, long long i, double *xs) {
-    if (P.layout == 0) {
+    if (GEN) {
+        b200e_smp::sample_point_fixed<NX>(P.pdf, P.gen_seed, (unsigned long long)(P.gen_first + i), xs);
+    } else if (P.layout == 0) {
         const double *xp = P.x + i * NX;
 #pragma unroll
         for (int j = 0; j < NX; j++) xs[j] = __ldg(xp + j);
@@ -196,11 +202,12 @@ __shared__ b200e_tabs sh_tab;
 enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
 
 // prob_func + integrator init for one lane: x -> (u0, p) via h, pdf weight, initial dt, FSAL k1
+template <bool GEN>
 __device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long long i, real *u, real *p,
                                                  real *k1, real &t, real &dt, real &le2old, double &wgt,
                                                  unsigned &nf) {
     double xs[NX];
-    load_point(P, i, xs);
+    load_point<GEN>(P, i, xs);
     wgt = P.weight_by_pdf ? pdf_weight(P, xs) : 1.0;
     real xr[NX], u0n[N], pn[B200E_DIM(NP)];
 #pragma unroll
@@ -373,7 +380,7 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     }
 }
 
-template <bool REDUCE, bool DYN>
+template <bool REDUCE, bool DYN, bool GEN>
 __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     // Work distribution.  Static: lane l owns points l, l+T, l+2T, ... (T = grid * block).  Dynamic:
     // whenever a warp refills, its idle lanes take the next consecutive points off the launch's counter;
@@ -455,7 +462,7 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 cur = next;
                 next = dyn ? P.npts : next + T;
                 L.nf0 = 0; L.nacc = 0; L.nrej = 0; L.failed = 0;
-                start_trajectory(P, cur, L.u, L.p, L.k1, L.t, L.dt, L.le2old, wgt, L.nf0);
+                start_trajectory<GEN>(P, cur, L.u, L.p, L.k1, L.t, L.dt, L.le2old, wgt, L.nf0);
                 L.state = (L.t < t1) ? LANE_ACTIVE : LANE_DONE;
             }
             act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
@@ -471,22 +478,27 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
 
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_nodes(const __grid_constant__ b200e_kparams P) {
-    tsit5_run<false, false>(P);
+    tsit5_run<false, false, false>(P);
 }
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_reduce(const __grid_constant__ b200e_kparams P) {
-    tsit5_run<true, false>(P);
+    tsit5_run<true, false, false>(P);
 }
 #if B200E_DYNAMIC
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_nodes_dyn(const __grid_constant__ b200e_kparams P) {
-    tsit5_run<false, true>(P);
+    tsit5_run<false, true, false>(P);
 }
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_reduce_dyn(const __grid_constant__ b200e_kparams P) {
-    tsit5_run<true, true>(P);
+    tsit5_run<true, true, false>(P);
 }
 #endif
+// MonteCarlo with the sampler in the kernel (b200e_reduce_generated)
+extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
+b200e_reduce_gen(const __grid_constant__ b200e_kparams P) {
+    tsit5_run<true, B200E_DYNAMIC != 0, true>(P);
+}
 
 #else
 // ------------------------------------------------------------------------------------------
@@ -497,7 +509,7 @@ b200e_reduce_dyn(const __grid_constant__ b200e_kparams P) {
 // ------------------------------------------------------------------------------------------
 constexpr int NK = B200E_NKKL;
 
-template <bool REDUCE, bool DYN>
+template <bool REDUCE, bool DYN, bool GEN>
 __device__ __forceinline__ void em_run(const b200e_kparams &P) {
     const long long T = (long long)gridDim.x * B200E_BLOCK;
     Accum A;
@@ -520,7 +532,7 @@ __device__ __forceinline__ void em_run(const b200e_kparams &P) {
             break;
         }
         double xs[NX];
-        load_point(P, i, xs);
+        load_point<GEN>(P, i, xs);
         const double wgt = P.weight_by_pdf ? pdf_weight(P, xs) : 1.0;
         real xr[NX], u0n[N], pn[B200E_DIM(NP)], u[N], p[B200E_DIM(NP)], z[NK];
 #pragma unroll
@@ -566,22 +578,27 @@ __device__ __forceinline__ void em_run(const b200e_kparams &P) {
 
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_nodes(const __grid_constant__ b200e_kparams P) {
-    em_run<false, false>(P);
+    em_run<false, false, false>(P);
 }
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_reduce(const __grid_constant__ b200e_kparams P) {
-    em_run<true, false>(P);
+    em_run<true, false, false>(P);
 }
 #if B200E_DYNAMIC
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_nodes_dyn(const __grid_constant__ b200e_kparams P) {
-    em_run<false, true>(P);
+    em_run<false, true, false>(P);
 }
 extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
 b200e_reduce_dyn(const __grid_constant__ b200e_kparams P) {
-    em_run<true, true>(P);
+    em_run<true, true, false>(P);
 }
 #endif
+// MonteCarlo with the sampler in the kernel (b200e_reduce_generated)
+extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
+b200e_reduce_gen(const __grid_constant__ b200e_kparams P) {
+    em_run<true, B200E_DYNAMIC != 0, true>(P);
+}
 #endif
 
 }  // namespace b200e
