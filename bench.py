@@ -261,26 +261,30 @@ def run_b200(args):
     make_samples(model, n, args.seed, rank * nb, xp.array)
     xd = h.device_array((n, nx)).upload(xp.array)
 
+    # the path's one exchange step: all-reduce of the 2*nout sums + 4 counters (counters < 2^53 as doubles)
     red = torch.zeros(2 * nout + 4, dtype=torch.float64, device="cuda")
+    red_h = torch.zeros(2 * nout + 4, dtype=torch.float64).pin_memory()
+    red_np = red_h.numpy()
+
+    def exchange(s, s2, c):
+        red_np[:nout] = s
+        red_np[nout:2 * nout] = s2
+        red_np[2 * nout:] = (c["nf"], c["naccept"], c["nreject"], c["nfail"])
+        red.copy_(red_h)
+        dist.all_reduce(red)
 
     def step_resident():
         s, s2, c = h.reduce_samples(xd, npts=n)
         st = h.last_stats()
         if world > 1:
-            red[:nout] = torch.from_numpy(s)
-            red[nout:2 * nout] = torch.from_numpy(s2)
-            red[2 * nout:] = torch.tensor([c["nf"], c["naccept"], c["nreject"], c["nfail"]], dtype=torch.float64)
-            dist.all_reduce(red)
+            exchange(s, s2, c)
         return s, s2, c, st
 
     def step_e2e():
         s, s2, c = h.reduce_samples(xp)  # pinned host buffer: H2D inside the call, sums come back D2H
         st = h.last_stats()
         if world > 1:
-            red[:nout] = torch.from_numpy(s)
-            red[nout:2 * nout] = torch.from_numpy(s2)
-            red[2 * nout:] = torch.tensor([c["nf"], c["naccept"], c["nreject"], c["nfail"]], dtype=torch.float64)
-            dist.all_reduce(red)
+            exchange(s, s2, c)
             torch.cuda.synchronize()
         return s, s2, c, st
 
@@ -290,10 +294,7 @@ def run_b200(args):
         s, s2, c = h.reduce_generated(args.seed, n, first_index=rank * n)
         st = h.last_stats()
         if world > 1:
-            red[:nout] = torch.from_numpy(s)
-            red[nout:2 * nout] = torch.from_numpy(s2)
-            red[2 * nout:] = torch.tensor([c["nf"], c["naccept"], c["nreject"], c["nfail"]], dtype=torch.float64)
-            dist.all_reduce(red)
+            exchange(s, s2, c)
             torch.cuda.synchronize()
         return s, s2, c, st
 
