@@ -56,6 +56,10 @@ Base.@kwdef struct EnsembleB200 <: SciMLBase.EnsembleAlgorithm
     model::B200Model
     devices::Vector{Int32} = Int32[]           # empty: current device; several: sharded + one NCCL all-reduce
     fp32::Bool = false
+    schedule::Int32 = 0                        # 0 dynamic work distribution, 1 static (bit-reproducible sums)
+    sampler::Symbol = :device                  # MonteCarlo: :device draws rand(d) in the kernel (counter-based
+                                               # stream, reproducible by b200e_sample_host); :host ships rand(d)
+    seed::UInt64 = 0x0000000000000000
 end
 
 pdfdim(d::Uniform) = PdfDim(1, 0, minimum(d), maximum(d), 0.0, 1.0)
@@ -80,7 +84,7 @@ function create_handle(exprob::ExpectationProblem, dists)
                     prob.tspan[1], prob.tspan[2], get(kw, :abstol, 1e-6), get(kw, :reltol, 1e-3),
                     get(kw, :dtmax, 0.0), 0.0, get(kw, :maxiters, 100000), pointer(pdf),
                     length(ens.devices), isempty(ens.devices) ? Ptr{Int32}(C_NULL) : pointer(ens.devices),
-                    0, 0, 0, 0, Cstring(C_NULL))
+                    0, 0, 0, 0, ens.schedule, 0, Cstring(C_NULL))
         rc = ccall((:b200e_create, LIB), Cint, (Ref{CModel}, Ref{Ptr{Cvoid}}), cm, h)
         rc == 0 || error("b200e_create: ", unsafe_string(ccall((:b200e_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
     end
@@ -111,6 +115,16 @@ function SciMLBase.solve(exprob::B200Problem, expalg::MonteCarlo; dists = exprob
     nout = exprob.S.ensemblealg.model.nout
     total = zeros(nout); s = zeros(nout); s2 = zeros(nout); c = Ref(Counters(0, 0, 0, 0))
     done = 0; n = expalg.trajectories
+    ens = exprob.S.ensemblealg
+    if ens.sampler === :device
+        # rand(d) hoisted into the kernel: samples 0 .. n-1 of the counter-based stream `seed`; the CPU arm gets
+        # the identical set from b200e_sample_host(model, seed, 0, n, 0, x)
+        check(ccall((:b200e_reduce_generated, LIB), Cint,
+                    (Ptr{Cvoid}, UInt64, UInt64, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Counters}),
+                    h, ens.seed, 0, n, s, s2, c), h)
+        c[].nfail > 0 && @warn "libb200expect: $(c[].nfail) trajectories aborted (maxiters / non-finite / dt underflow)"
+        total .+= s; done = n
+    end
     while done < n
         m = min(block, n - done)
         x = reduce(hcat, (rand(exprob.d) for _ in 1:m))          # dim x m: host-generated sample set
