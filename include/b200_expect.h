@@ -37,13 +37,14 @@
 extern "C" {
 #endif
 
-#define B200E_ABI_VERSION 2
+#define B200E_ABI_VERSION 3
 
 /* limits (compile-time dims of the generated kernel) */
 #define B200E_MAX_STATE 16
 #define B200E_MAX_PARAM 32
 #define B200E_MAX_X 32
-#define B200E_MAX_OUT 16
+#define B200E_MAX_OUT 64
+#define B200E_MAX_SAVE 64
 #define B200E_MAX_KKL 32
 
 enum {
@@ -88,6 +89,11 @@ typedef struct {
  *                      real* u0_or_Z, real* p);                 (h, expectation.jl:176, :216)
  *   B200E_FN void observable(const real* u_end, const real* p, real t_end, real* out); (g, end-state form)
  *   B200E_FN void diffusion(real* g, const real* u, const real* p, real t);           (EM only; scalar noise)
+ *   B200E_FN void observable_at(int k, real t_k, const real* u_k, const real* p, real* out_k);
+ *                      (g built from the solution at saved times -- sol(t_k), sol[i, :] with saveat,
+ *                       docs/src/tutorials/introduction.md:53, :192, :207-212: called once per save time, in
+ *                       order, with the state interpolated by Tsit5's free 4th-order interpolant; writes the
+ *                       nout / nsave outputs of slot k.  Replaces `observable` when nsave > 0.)
  *
  * u0/p outputs of hmap are pre-filled with the nominal values, so hmap only writes what it changes.
  */
@@ -114,7 +120,8 @@ typedef struct {
     int32_t refill_threshold; /* lanes of a warp that must be idle before the warp reloads (1..32); 0 = automatic */
     int32_t chunk_points;     /* host-pointer calls are pipelined in chunks of this many points */
     int32_t schedule;         /* B200E_SCHED_* */
-    int32_t _reserved;
+    int32_t nsave;            /* > 0: time-sampled observable (Tsit5 only), nout = nsave * outputs per save time */
+    const double *save_times; /* nsave ascending times in [t0, t1] (saveat / the arguments of sol(t)) */
     const char *cache_dir;    /* cubin cache directory, NULL -> $B200E_CACHE_DIR or disabled */
 } b200e_model;
 

@@ -39,7 +39,8 @@ struct CModel            # b200e_model (field order = include/b200_expect.h)
     pdf::Ptr{PdfDim}
     n_devices::Int32; devices::Ptr{Int32}
     block_size::Int32; blocks_per_sm::Int32; refill_threshold::Int32; chunk_points::Int32
-    schedule::Int32; _reserved::Int32   # 0 dynamic (default), 1 static = bit-reproducible sums
+    schedule::Int32                     # 0 dynamic (default), 1 static = bit-reproducible sums
+    nsave::Int32; save_times::Ptr{Float64}   # time-sampled observables (saveat / sol(t)): nout = nsave * outputs per time
     cache_dir::Cstring
 end
 struct Counters; nf::UInt64; naccept::UInt64; nreject::UInt64; nfail::UInt64; end
@@ -84,7 +85,7 @@ function create_handle(exprob::ExpectationProblem, dists)
                     prob.tspan[1], prob.tspan[2], get(kw, :abstol, 1e-6), get(kw, :reltol, 1e-3),
                     get(kw, :dtmax, 0.0), 0.0, get(kw, :maxiters, 100000), pointer(pdf),
                     length(ens.devices), isempty(ens.devices) ? Ptr{Int32}(C_NULL) : pointer(ens.devices),
-                    0, 0, 0, 0, ens.schedule, 0, Cstring(C_NULL))
+                    0, 0, 0, 0, ens.schedule, 0, Ptr{Float64}(C_NULL), Cstring(C_NULL))
         rc = ccall((:b200e_create, LIB), Cint, (Ref{CModel}, Ref{Ptr{Cvoid}}), cm, h)
         rc == 0 || error("b200e_create: ", unsafe_string(ccall((:b200e_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
     end

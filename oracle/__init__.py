@@ -21,7 +21,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libexpect_oracle.so")
 
-ORC_MAX_STATE, ORC_MAX_PARAM, ORC_MAX_X, ORC_MAX_OUT, ORC_MAX_KKL = 16, 32, 32, 16, 32
+ORC_MAX_STATE, ORC_MAX_PARAM, ORC_MAX_X, ORC_MAX_OUT, ORC_MAX_KKL, ORC_MAX_SAVE = 16, 32, 32, 64, 32, 64
 PDF_NONE, PDF_UNIFORM, PDF_NORMAL, PDF_TRUNCNORMAL = 0, 1, 2, 3
 SOLVER_TSIT5, SOLVER_EM = 0, 1
 
@@ -47,6 +47,7 @@ class Problem(C.Structure):
         ("dtmax", C.c_double), ("dt_fixed", C.c_double),
         ("maxiters", C.c_int64),
         ("pdf", C.POINTER(PdfDim)),
+        ("nsave", C.c_int32), ("_pad", C.c_int32), ("save_t", C.POINTER(C.c_double)), ("obs_at", C.c_void_p),
     ]
 
 
@@ -114,19 +115,28 @@ class OracleProblem:
 
     @classmethod
     def from_source(cls, src: str, *, nstate, nparam, nx, nout, u0, p, tspan, solver=SOLVER_TSIT5,
-                    n_kkl=0, pdf=None, **overrides) -> "OracleProblem":
+                    n_kkl=0, pdf=None, save_times=(), **overrides) -> "OracleProblem":
         """Compile a model written in the shared C/CUDA dialect (see models.py) with gcc and wrap it.
 
         The source defines ``rhs``, ``hmap``, ``observable`` (and ``diffusion`` for EM) with
         ``B200E_FN`` linkage and ``real`` scalars; here ``real`` is double."""
-        so = _compile_model(src, has_diffusion=(solver == SOLVER_EM))
+        save_times = [float(t) for t in save_times]
+        so = _compile_model(src, has_diffusion=(solver == SOLVER_EM), has_obs_at=bool(save_times))
         m = C.CDLL(so)
         st = Problem()
         st.nstate, st.nparam, st.nx, st.nout = nstate, nparam, nx, nout
         st.solver, st.n_kkl = solver, n_kkl
         st.rhs = C.cast(m.orc_model_rhs, C.c_void_p)
         st.hmap = C.cast(m.orc_model_hmap, C.c_void_p)
-        st.obs = C.cast(m.orc_model_obs, C.c_void_p)
+        keep_extra = []
+        if save_times:
+            assert nout % len(save_times) == 0 and len(save_times) <= ORC_MAX_SAVE and nout <= ORC_MAX_OUT
+            st.obs_at = C.cast(m.orc_model_obs_at, C.c_void_p)
+            ta = (C.c_double * len(save_times))(*save_times)
+            st.nsave, st.save_t = len(save_times), C.cast(ta, C.POINTER(C.c_double))
+            keep_extra.append(ta)
+        else:
+            st.obs = C.cast(m.orc_model_obs, C.c_void_p)
         if solver == SOLVER_EM:
             st.diffusion = C.cast(m.orc_model_diffusion, C.c_void_p)
         u0a = (C.c_double * max(1, nstate))(*[float(v) for v in u0])
@@ -134,7 +144,7 @@ class OracleProblem:
         st.u0_nom, st.p_nom = C.cast(u0a, C.POINTER(C.c_double)), C.cast(pa, C.POINTER(C.c_double))
         st.t0, st.t1 = float(tspan[0]), float(tspan[1])
         st.abstol, st.reltol, st.maxiters = 1e-6, 1e-3, 100000
-        self = cls(st, keep=[m, u0a, pa])
+        self = cls(st, keep=[m, u0a, pa] + keep_extra)
         if pdf is not None:
             self.set_pdf(pdf)
         self.configure(**overrides)
@@ -222,15 +232,21 @@ typedef double real;
 _EPILOGUE = r"""
 void orc_model_rhs(double *du, const double *u, const double *p, double t) { rhs(du, u, p, t); }
 void orc_model_hmap(const double *x, const double *u0n, const double *pn, double *u0, double *p) { hmap(x, u0n, pn, u0, p); }
+"""
+_EPILOGUE_OBS = r"""
 void orc_model_obs(const double *u, const double *p, double t, double *out) { observable(u, p, t, out); }
+"""
+_EPILOGUE_OBS_AT = r"""
+void orc_model_obs_at(int k, double t, const double *u, const double *p, double *out) { observable_at(k, t, u, p, out); }
 """
 _EPILOGUE_DIFF = r"""
 void orc_model_diffusion(double *g, const double *u, const double *p, double t) { diffusion(g, u, p, t); }
 """
 
 
-def _compile_model(src: str, has_diffusion: bool) -> str:
-    full = _PRELUDE + src + _EPILOGUE + (_EPILOGUE_DIFF if has_diffusion else "")
+def _compile_model(src: str, has_diffusion: bool, has_obs_at: bool = False) -> str:
+    full = (_PRELUDE + src + _EPILOGUE + (_EPILOGUE_OBS_AT if has_obs_at else _EPILOGUE_OBS)
+            + (_EPILOGUE_DIFF if has_diffusion else ""))
     h = hashlib.sha256(full.encode()).hexdigest()[:16]
     d = os.path.join(tempfile.gettempdir(), "b200e_oracle_models")
     os.makedirs(d, exist_ok=True)

@@ -36,6 +36,18 @@ static const double BT1 = -0.00178001105222577714, BT2 = -0.0008164344596567469,
                     BT5 = 0.5823571654525552, BT6 = -0.45808210592918697,
                     BT7 = 0.015151515151515152;
 
+/* Tsit5's free 4th-order interpolant (Tsitouras 2011; OrdinaryDiffEq's tsit_interpolants):
+ *   u(t + theta dt) = u + dt sum_i b_i(theta) k_i,
+ *   b_1 = theta (r11 + theta (r12 + theta (r13 + theta r14))),  b_i = theta^2 (ri2 + theta (ri3 + theta ri4)) */
+static const double RI[7][4] = {
+    {1.0, -2.763706197274826, 2.9132554618219126, -1.0530884977290216},
+    {0.0, 0.13169999999999998, -0.2234, 0.1017},
+    {0.0, 3.9302962368947516, -5.941033872131505, 2.490627285651253},
+    {0.0, -12.411077166933676, 30.33818863028232, -16.548102889244902},
+    {0.0, 37.50931341651104, -88.1789048947664, 47.37952196281928},
+    {0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661},
+    {0.0, 1.5, -4.0, 2.5}};
+
 /* PI controller defaults for an order-5 explicit RK pair (OrdinaryDiffEq) */
 static const double BETA1 = 7.0 / 50.0, BETA2 = 2.0 / 25.0, GAMMA = 9.0 / 10.0;
 static const double QMIN = 1.0 / 5.0, QMAX = 10.0, QOLDINIT = 1e-4;
@@ -96,7 +108,7 @@ double orc_kkl_w(const double *z, int n, double t) {
 
 /* ---- adaptive Tsit5, one trajectory.  Returns 0 ok / 1 failed; u updated in place ---- */
 static int tsit5_solve(const orc_problem *pb, double *u, const double *p, uint64_t *nf_out,
-                       uint64_t *nacc_out, uint64_t *nrej_out) {
+                       uint64_t *nacc_out, uint64_t *nrej_out, double *save_out) {
     const int n = pb->nstate;
     const double t0 = pb->t0, t1 = pb->t1;
     const double abstol = pb->abstol, reltol = pb->reltol;
@@ -108,6 +120,14 @@ static int tsit5_solve(const orc_problem *pb, double *u, const double *p, uint64
     uint64_t nf = 0, nacc = 0, nrej = 0;
     int failed = 0;
     double t = t0;
+    /* saveat: slots whose time is t0 hold the initial state (save_start) */
+    const int nsave = save_out ? pb->nsave : 0;
+    const int nps = nsave > 0 ? pb->nout / nsave : 0;
+    int ksave = 0;
+    while (ksave < nsave && pb->save_t[ksave] <= t0) {
+        pb->obs_at(ksave, pb->save_t[ksave], u, p, save_out + (size_t)ksave * nps);
+        ksave++;
+    }
 
     /* Hairer-Wanner initial step as OrdinaryDiffEq's ode_determine_initdt does it */
     double dt;
@@ -201,6 +221,27 @@ static int tsit5_solve(const orc_problem *pb, double *u, const double *p, uint64
             double ttmp = t + dt;
             /* fixed_t_for_floatingpoint_error! */
             if (fabs(ttmp - t1) < 100.0 * ulp_of(fmax(t, t1))) ttmp = t1;
+            /* saveat / sol(t): every save time inside (t, ttmp] */
+            while (ksave < nsave && pb->save_t[ksave] <= ttmp) {
+                const double ts = pb->save_t[ksave];
+                double us[ORC_MAX_STATE];
+                if (ts >= ttmp) {
+                    for (int i = 0; i < n; i++) us[i] = unew[i];
+                } else {
+                    const double th = (ts - t) / dt;
+                    double b[7];
+                    for (int j = 0; j < 7; j++)
+                        b[j] = th * (RI[j][0] + th * (RI[j][1] + th * (RI[j][2] + th * RI[j][3])));
+                    const double *ks[7] = {k1, k2, k3, k4, k5, k6, k7};
+                    for (int i = 0; i < n; i++) {
+                        double acc = 0;
+                        for (int j = 0; j < 7; j++) acc += b[j] * ks[j][i];
+                        us[i] = u[i] + dt * acc;
+                    }
+                }
+                pb->obs_at(ksave, ts, us, p, save_out + (size_t)ksave * nps);
+                ksave++;
+            }
             t = ttmp;
             for (int i = 0; i < n; i++) { u[i] = unew[i]; k1[i] = k7[i]; } /* FSAL */
             dt = fmin(dtmax, dtnew); /* calc_dt_propose! */
@@ -211,6 +252,8 @@ static int tsit5_solve(const orc_problem *pb, double *u, const double *p, uint64
             nrej++;
         }
     }
+    /* a trajectory that aborted never reached the remaining save times: their slots are NaN */
+    for (int k = ksave * nps; k < nsave * nps; k++) save_out[k] = NAN;
     *nf_out += nf;
     *nacc_out += nacc;
     *nrej_out += nrej;
@@ -261,9 +304,9 @@ static int solve_point_steps(const orc_problem *pb, const double *x, int weight_
         for (int i = 0; i < pb->nstate; i++) u[i] = pb->u0_nom[i];
         for (int i = 0; i < pb->nparam; i++) p[i] = pb->p_nom[i];
         pb->hmap(x, pb->u0_nom, pb->p_nom, u, p);
-        failed = tsit5_solve(pb, u, p, &nf, &nacc, &nrej);
+        failed = tsit5_solve(pb, u, p, &nf, &nacc, &nrej, pb->nsave > 0 ? out : NULL);
     }
-    pb->obs(u, p, pb->t1, out);
+    if (!(pb->solver == ORC_SOLVER_TSIT5 && pb->nsave > 0)) pb->obs(u, p, pb->t1, out);
     if (weight_by_pdf && pb->pdf) {
         /* expectation.jl:180: g(sol, p) * pdf(d, x) */
         double w = exp(orc_logpdf(pb->pdf, pb->nx, x));

@@ -29,7 +29,8 @@ extern "C" {
 #define ORC_MAX_STATE 16
 #define ORC_MAX_PARAM 32
 #define ORC_MAX_X 32
-#define ORC_MAX_OUT 16
+#define ORC_MAX_OUT 64
+#define ORC_MAX_SAVE 64
 #define ORC_MAX_KKL 32
 
 typedef void (*orc_rhs_fn)(double *du, const double *u, const double *p, double t);
@@ -39,6 +40,11 @@ typedef void (*orc_map_fn)(const double *x, const double *u0_nom, const double *
                            double *u0_or_z, double *p);
 /* g(sol, p) restricted to end-state observables: g(u(t1), p, t1) -> out[nout] */
 typedef void (*orc_obs_fn)(const double *u_end, const double *p, double t_end, double *out);
+
+/* g(sol, p) built from the solution at saved times (sol(t_k), sol[i, :] with saveat; reference
+ * docs/src/tutorials/introduction.md:53, :192, :207-212): called once per save time, in order, with the
+ * interpolated state; writes the nout / nsave outputs of slot k */
+typedef void (*orc_obs_at_fn)(int k, double t_k, const double *u_k, const double *p, double *out_k);
 
 enum { ORC_PDF_NONE = 0, ORC_PDF_UNIFORM = 1, ORC_PDF_NORMAL = 2, ORC_PDF_TRUNCNORMAL = 3 };
 
@@ -68,6 +74,14 @@ typedef struct {
     double dt_fixed;       /* EM step */
     int64_t maxiters;      /* <=0 -> 100000 */
     const orc_pdf_dim *pdf; /* nx entries, or NULL (weight 1) */
+    /* time-sampled observables (Tsit5 only): nsave > 0 -> nout = nsave * (outputs per save time), the
+     * outputs come from obs_at at the ascending times save_t[0..nsave) in [t0, t1] (obs is not called).
+     * States between steps come from Tsit5's free 4th-order interpolant, as OrdinaryDiffEq's saveat /
+     * sol(t) do; a save time equal to the end of a step takes the step's own end state. */
+    int32_t nsave;
+    int32_t _pad;
+    const double *save_t;
+    orc_obs_at_fn obs_at;
 } orc_problem;
 
 typedef struct {

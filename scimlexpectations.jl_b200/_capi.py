@@ -17,8 +17,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libb200expect.so")
 
-ABI_VERSION = 2
-MAX_STATE, MAX_PARAM, MAX_X, MAX_OUT, MAX_KKL = 16, 32, 32, 16, 32
+ABI_VERSION = 3
+MAX_STATE, MAX_PARAM, MAX_X, MAX_OUT, MAX_KKL, MAX_SAVE = 16, 32, 32, 64, 32, 64
 OK, ERR_INVALID, ERR_COMPILE, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
 SOLVER_TSIT5, SOLVER_EM = 0, 1
 FP64, FP32 = 0, 1
@@ -69,7 +69,7 @@ class Model(C.Structure):
         ("devices", C.POINTER(C.c_int32)),
         ("block_size", C.c_int32), ("blocks_per_sm", C.c_int32),
         ("refill_threshold", C.c_int32), ("chunk_points", C.c_int32),
-        ("schedule", C.c_int32), ("_reserved", C.c_int32),
+        ("schedule", C.c_int32), ("nsave", C.c_int32), ("save_times", C.POINTER(C.c_double)),
         ("cache_dir", C.c_char_p),
     ]
 
@@ -202,6 +202,7 @@ class ModelSpec:
     refill_threshold: int = 0
     chunk_points: int = 0
     schedule: int = 0            # SCHED_DYNAMIC (default) / SCHED_STATIC (bit-reproducible sums)
+    save_times: Sequence[float] = ()  # time-sampled observable: saveat / the arguments of sol(t); nout = len * outputs per time
     cache_dir: Optional[str] = None
 
     def replace(self, **kw) -> "ModelSpec":
@@ -241,6 +242,10 @@ class ModelSpec:
         m.block_size, m.blocks_per_sm = int(self.block_size), int(self.blocks_per_sm)
         m.refill_threshold, m.chunk_points = int(self.refill_threshold), int(self.chunk_points)
         m.schedule = int(self.schedule)
+        if len(self.save_times):
+            ta = (C.c_double * len(self.save_times))(*[float(t) for t in self.save_times])
+            keep.append(ta)
+            m.nsave, m.save_times = len(self.save_times), C.cast(ta, C.POINTER(C.c_double))
         cache = self.cache_dir if self.cache_dir is not None else default_cache_dir()
         if cache:
             cb = cache.encode()

@@ -145,11 +145,14 @@ def rand(d: GenericDistribution): return d.rand_func()
 # ---------------------------------------------------------------------------------------------
 @dataclass
 class ODEProblem:
-    """``ODEProblem(f, u0, tspan, p)``; ``f`` is CUDA source defining ``rhs(du,u,p,t)``."""
+    """``ODEProblem(f, u0, tspan, p; saveat)``; ``f`` is CUDA source defining ``rhs(du,u,p,t)``.
+    ``saveat`` (docs/src/tutorials/introduction.md:207-212) lists the times at which the observable sees
+    the solution: ``g`` is then an ``observable_at`` source and ``nout = len(saveat) * outputs per time``."""
     f: str
     u0: Sequence[float]
     tspan: Sequence[float]
     p: Sequence[float] = ()
+    saveat: Sequence[float] = ()
 
 
 @dataclass
@@ -268,7 +271,7 @@ class ExpectationProblem:
                          pdf=self.d.table(), fp_mode=FP32 if ens.fp32 else FP64, devices=ens.devices,
                          block_size=ens.block_size, blocks_per_sm=ens.blocks_per_sm,
                          refill_threshold=ens.refill_threshold, chunk_points=ens.chunk_points,
-                         schedule=ens.schedule)
+                         schedule=ens.schedule, save_times=tuple(float(t) for t in prob.saveat))
 
     def handle(self) -> _capi.Handle:
         spec = self.model_spec()

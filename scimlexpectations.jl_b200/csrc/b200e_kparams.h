@@ -7,6 +7,7 @@
 #define B200E_KP_MAX_STATE 16
 #define B200E_KP_MAX_PARAM 32
 #define B200E_KP_MAX_X 32
+#define B200E_KP_MAX_SAVE 64
 
 // device form of one factor of the product density: logpdf(x) = logc - 0.5*((x-mu)*inv_sigma)^2
 // inside [lo,hi], -inf outside.  logc folds -log(sigma) - log(2pi)/2 - log(cdf(hi)-cdf(lo))
@@ -50,6 +51,7 @@ struct b200e_kparams {
     double u0_nom[B200E_KP_MAX_STATE];
     double p_nom[B200E_KP_MAX_PARAM];
     b200e_kpdf pdf[B200E_KP_MAX_X];
+    double save_t[B200E_KP_MAX_SAVE];  // time-sampled observables: ascending save times (B200E_NSAVE of them)
 };
 
 #endif

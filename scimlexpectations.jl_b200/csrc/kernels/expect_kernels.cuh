@@ -69,7 +69,7 @@ __device__ __forceinline__ void load_point(const b200e_kparams &P, long long i, 
 // TRAJECTORY (not per step), so they live in shared memory, one conflict-free column per thread,
 // and stay out of the register budget of the step loop (registers decide how many warps are
 // resident, and resident warps are what hides the FP64 dependency chains).
-constexpr bool ACC_SMEM = (NACC * 8 + 4 * 8) * B200E_BLOCK <= 32768;
+constexpr bool ACC_SMEM = (NACC * 8 + 4 * 8) * B200E_BLOCK <= 40960;  // the host sizes the block so that this holds
 __shared__ double sh_acc[ACC_SMEM ? NACC : 1][B200E_BLOCK];
 __shared__ unsigned long long sh_cnt[ACC_SMEM ? 4 : 1][B200E_BLOCK];
 
@@ -90,7 +90,32 @@ struct Accum {
     }
 };
 
-// observable + weight + (store | accumulate): output_func of the reference
+#ifndef B200E_NSAVE
+#define B200E_NSAVE 0
+#endif
+constexpr int NSAVE = B200E_NSAVE;
+constexpr int NPS = NSAVE > 0 ? NOUT / NSAVE : NOUT;  // outputs per save time
+
+// weight + (store | accumulate) of outputs [first, first + count) of point i: output_func of the reference
+template <bool REDUCE>
+__device__ __forceinline__ void emit_values(const b200e_kparams &P, long long i, int first, int count, const real *out,
+                                            double wgt, Accum &A) {
+    for (int j = 0; j < count; j++) {
+        double v = (double)out[j];
+        if (P.weight_by_pdf) v *= wgt;
+        const int k = first + j;
+        if (REDUCE) {
+            A.val(k) += v;
+            A.val(NOUT + k) = fma(v, v, A.val(NOUT + k));
+        } else {
+            if (P.layout == 0) P.dx[i * NOUT + k] = v;
+            else P.dx[(long long)k * P.ld + i] = v;
+        }
+    }
+}
+
+#if B200E_NSAVE == 0
+// end-state observable g(sol[:, end], p)
 template <bool REDUCE>
 __device__ __forceinline__ void emit(const b200e_kparams &P, long long i, const real *u, const real *p,
                                      double wgt, Accum &A) {
@@ -109,6 +134,24 @@ __device__ __forceinline__ void emit(const b200e_kparams &P, long long i, const 
         }
     }
 }
+#else
+// time-sampled observable: slot k of g(sol, p) from the state at save time k (sol(t_k), sol[i, :] with saveat)
+template <bool REDUCE>
+__device__ __forceinline__ void emit_slot(const b200e_kparams &P, long long i, int k, real ts, const real *us,
+                                          const real *p, double wgt, Accum &A) {
+    real out[NPS];
+    observable_at(k, ts, us, p, out);
+    emit_values<REDUCE>(P, i, k * NPS, NPS, out, wgt, A);
+}
+// a trajectory that aborted never reached its remaining save times: their slots are NaN
+template <bool REDUCE>
+__device__ __forceinline__ void emit_missing(const b200e_kparams &P, long long i, int kfrom, double wgt, Accum &A) {
+    real out[NPS];
+#pragma unroll
+    for (int j = 0; j < NPS; j++) out[j] = (real)__longlong_as_double(0x7ff8000000000000LL);
+    for (int k = kfrom; k < NSAVE; k++) emit_values<REDUCE>(P, i, k * NPS, NPS, out, 1.0, A);
+}
+#endif
 
 // warp shuffle + shared-memory block reduction; only per-block partials reach HBM.  Counters are
 // folded in both modes; the value accumulators only in reduce mode.
@@ -118,33 +161,34 @@ __device__ __forceinline__ void block_reduce_store(const b200e_kparams &P, Accum
     __shared__ unsigned long long scnt[NWARPS][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long cnt[4];
-    double acc[NACC];
 #pragma unroll
     for (int k = 0; k < 4; k++) cnt[k] = A.cnt(k);
 #pragma unroll
-    for (int k = 0; k < NACC; k++) acc[k] = A.val(k);
-#pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        if (REDUCE) {
-#pragma unroll
-            for (int k = 0; k < NACC; k++) acc[k] += __shfl_down_sync(B200E_FULL, acc[k], off);
-        }
 #pragma unroll
         for (int k = 0; k < 4; k++) cnt[k] += __shfl_down_sync(B200E_FULL, cnt[k], off);
     }
     if (lane == 0) {
-        if (REDUCE) {
-#pragma unroll
-            for (int k = 0; k < NACC; k++) sacc[warp][k] = acc[k];
-        }
 #pragma unroll
         for (int k = 0; k < 4; k++) scnt[warp][k] = cnt[k];
     }
+    if (REDUCE) {
+        // one column at a time: a wide observable (2 nout columns) must not sit in registers all at once
+#pragma unroll 1
+        for (int k = 0; k < NACC; k++) {
+            double v = A.val(k);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(B200E_FULL, v, off);
+            if (lane == 0) sacc[warp][k] = v;
+        }
+    }
     __syncthreads();
-    if (REDUCE && threadIdx.x < NACC) {
-        double t = 0.0;
-        for (int w = 0; w < NWARPS; w++) t += sacc[w][threadIdx.x];
-        P.partials[(long long)blockIdx.x * NACC + threadIdx.x] = t;
+    if (REDUCE) {
+        for (int k = threadIdx.x; k < NACC; k += B200E_BLOCK) {  // NACC may exceed a small block
+            double t = 0.0;
+            for (int w = 0; w < NWARPS; w++) t += sacc[w][k];
+            P.partials[(long long)blockIdx.x * NACC + k] = t;
+        }
     }
     if (threadIdx.x < 4) {
         const int k = threadIdx.x;
@@ -278,11 +322,21 @@ struct Lane {
     int state;
     int failed;  // 0 ok, 1 aborted, 2 NaN error estimate seen: abort at the next loop header
     unsigned nf0, nacc, nrej;  // nf = nf0 (initial-step evaluations) + 6 * (nacc + nrej)
+    int ksave;                 // time-sampled observables: next save slot
 };
 
+// what the accept branch needs to emit save slots (unused, and compiled away, when B200E_NSAVE == 0)
+struct SaveCtx {
+    const b200e_kparams &P;
+    long long point;
+    double wgt;
+    Accum &A;
+};
+
+template <bool REDUCE>
 __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dtmax,
                                            const real abstol, const real reltol, const real snap_tol,
-                                           const int maxiters, const real one_plus_eps) {
+                                           const int maxiters, const real one_plus_eps, const SaveCtx &S) {
     real *u = L.u, *k1 = L.k1, *p = L.p;
     const real t = L.t;
     // ---- loopheader!: a NaN error estimate in the previous attempt, the iteration cap, or a step
@@ -348,6 +402,40 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     // 1/N is a DFMA immediate when N is a power of two
     const real e2 = ss * (((N & (N - 1)) == 0) ? R_(lit::inv_n) : K_(inv_n));  // EEst^2
     const bool accept = le_nonneg(e2, one_plus_eps);  // sqrt(e2) <= 1  <=>  e2 <= nextafter(1); false for a NaN
+#if B200E_NSAVE > 0
+    // before the controller, while the stages are still live anyway (keeps them out of its register budget)
+    if (accept) {
+        const real left0 = t1 - tnext;
+        const real tnew = lt_nonneg(abs_bits(left0), snap_tol) ? t1 : tnext;  // the same snap as below
+        // saveat / sol(t): every save time inside (t, t_new] from Tsit5's free 4th-order interpolant
+        //   u(t + th dt) = u + sum_i b_i(th) kd_i,  b_1 = th (r11 + th (r12 + th (r13 + th r14))),
+        //   b_i = th^2 (ri2 + th (ri3 + th ri4))   (Tsitouras 2011; OrdinaryDiffEq's tsit_interpolants);
+        // a save time at the end of the step takes the step's own end state
+        while (L.ksave < NSAVE && (real)S.P.save_t[L.ksave] <= tnew) {
+            const real ts = (real)S.P.save_t[L.ksave];
+            real us[N];
+            if (ts >= tnew) {
+#pragma unroll
+                for (int i = 0; i < N; i++) us[i] = un[i];
+            } else {
+                const real th = (ts - t) / dt, th2 = th * th;
+                const real b1 = th * (R_(1.0) + th * (R_(-2.763706197274826) + th * (R_(2.9132554618219126) + th * R_(-1.0530884977290216))));
+                const real b2 = th2 * (R_(0.13169999999999998) + th * (R_(-0.2234) + th * R_(0.1017)));
+                const real b3 = th2 * (R_(3.9302962368947516) + th * (R_(-5.941033872131505) + th * R_(2.490627285651253)));
+                const real b4 = th2 * (R_(-12.411077166933676) + th * (R_(30.33818863028232) + th * R_(-16.548102889244902)));
+                const real b5 = th2 * (R_(37.50931341651104) + th * (R_(-88.1789048947664) + th * R_(47.37952196281928)));
+                const real b6 = th2 * (R_(-27.896526289197286) + th * (R_(65.09189467479366) + th * R_(-34.87065786149661)));
+                const real b7 = th2 * (R_(1.5) + th * (R_(-4.0) + th * R_(2.5)));
+#pragma unroll
+                for (int i = 0; i < N; i++)
+                    us[i] = u[i] + (b1 * kd1[i] + b2 * kd2[i] + b3 * kd3[i] + b4 * kd4[i] + b5 * kd5[i] + b6 * kd6[i] +
+                                    b7 * (dt * k7[i]));
+            }
+            emit_slot<REDUCE>(S.P, S.point, L.ksave, ts, us, p, S.wgt, S.A);
+            L.ksave++;
+        }
+    }
+#endif
 
     // ---- PI controller in log space on e2: one log + one exp instead of two pow + sqrt ----
     // accept:  1/q = gamma * qold^b2 / EEst^b1  clamped to [qmin, qmax]
@@ -396,7 +484,7 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     Lane L;
     L.t = R_(0.0); L.dt = R_(0.0); L.le2old = R_(0.0);
     L.state = LANE_EMPTY; L.failed = 0;
-    L.nf0 = 0; L.nacc = 0; L.nrej = 0;
+    L.nf0 = 0; L.nacc = 0; L.nrej = 0; L.ksave = 0;
     double wgt = 1.0;
     Accum A;
     A.init();
@@ -443,7 +531,11 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 tune = false;
             }
             if (L.state == LANE_DONE) {
+#if B200E_NSAVE > 0
+                emit_missing<REDUCE>(P, cur, L.ksave, wgt, A);
+#else
                 emit<REDUCE>(P, cur, L.u, L.p, wgt, A);
+#endif
                 if (!REDUCE && P.steps) P.steps[cur] = (int)(L.nacc + L.nrej);
                 A.count(L.nf0 + 6u * (L.nacc + L.nrej), L.nacc, L.nrej, L.failed ? 1u : 0u);
                 L.state = LANE_EMPTY;
@@ -464,13 +556,18 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 L.nf0 = 0; L.nacc = 0; L.nrej = 0; L.failed = 0;
                 start_trajectory<GEN>(P, cur, L.u, L.p, L.k1, L.t, L.dt, L.le2old, wgt, L.nf0);
                 L.state = (L.t < t1) ? LANE_ACTIVE : LANE_DONE;
+#if B200E_NSAVE > 0
+                // save times at t0 hold the initial state (save_start)
+                for (L.ksave = 0; L.ksave < NSAVE && (real)P.save_t[L.ksave] <= L.t; L.ksave++)
+                    emit_slot<REDUCE>(P, cur, L.ksave, (real)P.save_t[L.ksave], L.u, L.p, wgt, A);
+#endif
             }
             act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
         }
         if (act_m == 0u) continue;
         // ---- step phase: a tight loop, one vote per step, until some lane finishes ----
         do {
-            if (L.state == LANE_ACTIVE) tsit5_step(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps);
+            if (L.state == LANE_ACTIVE) tsit5_step<REDUCE>(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps, SaveCtx{P, cur, wgt, A});
         } while (__ballot_sync(B200E_FULL, L.state == LANE_ACTIVE) == act_m);
     }
     block_reduce_store<REDUCE>(P, A);

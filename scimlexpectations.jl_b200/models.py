@@ -46,6 +46,15 @@ def observable_components(idx):
             f"{body}\n}}\n")
 
 
+def observable_at_components(idx):
+    """Time-sampled observable: ``g(sol,p) = sol[idx, :]`` with ``saveat`` resp. ``[sol(t_k)[i] for ...]``
+    (docs/src/tutorials/introduction.md:53, :192, :207-212): slot k holds the components ``idx`` of the
+    state at the k-th save time (``ModelSpec.save_times``); ``nout = len(save_times) * len(idx)``."""
+    body = "\n".join(f"    out[{j}] = u[{int(i)}];" for j, i in enumerate(idx))
+    return ("B200E_FN void observable_at(int k, real t, const real* u, const real* p, real* out) {\n"
+            f"{body}\n}}\n")
+
+
 # ---- C1 / C2 ----------------------------------------------------------------------------------
 # f(du,u,p,t) with A = [0 1; -p1 -p2] captured at construction from the nominal p = [1, 2]
 # (README.md:38-39): the matrix does not follow the remade parameters.
@@ -62,6 +71,31 @@ def linear2(**kw) -> ModelSpec:
     return ModelSpec(source=src, nstate=2, nparam=2, nx=2, nout=2, u0=[1.0, 1.0], p=[1.0, 2.0],
                      tspan=(0.0, 3.0),
                      pdf=[(PDF_UNIFORM, 1.0, 10.0, 0.0, 1.0), (PDF_TRUNCNORMAL, 0.0, 6.0, 3.0, 1.0)]).replace(**kw)
+
+
+def linear2_saveat(**kw) -> ModelSpec:
+    """The README problem observed at six times (``g(sol,p) = sol[:, :]`` with saveat): both components."""
+    ts = (0.0, 0.5, 1.0, 1.7, 2.5, 3.0)
+    src = _LINEAR2_RHS + hmap_scatter(u0_from_x=[(0, 0), (1, 1)]) + observable_at_components([0, 1])
+    return ModelSpec(source=src, nstate=2, nparam=2, nx=2, nout=2 * len(ts), u0=[1.0, 1.0], p=[1.0, 2.0],
+                     tspan=(0.0, 3.0), save_times=ts,
+                     pdf=[(PDF_UNIFORM, 1.0, 10.0, 0.0, 1.0), (PDF_TRUNCNORMAL, 0.0, 6.0, 3.0, 1.0)]).replace(**kw)
+
+
+# docs/src/tutorials/introduction.md:14-24, :207-212: u' = p u, u0 ~ Uniform(0, 10), p = -0.3, tspan (0, 10),
+# saveat = 0:0.5:10, g(sol, p) = sol[1, :]; analytical E = exp(p t) * mean(u0)
+_SCALAR_GROWTH_RHS = """
+B200E_FN void rhs(real* du, const real* u, const real* p, real t) {
+    du[0] = p[0] * u[0];
+}
+"""
+
+
+def growth_saveat(**kw) -> ModelSpec:
+    ts = tuple(0.5 * k for k in range(21))
+    src = _SCALAR_GROWTH_RHS + hmap_scatter(u0_from_x=[(0, 0)]) + observable_at_components([0])
+    return ModelSpec(source=src, nstate=1, nparam=1, nx=1, nout=len(ts), u0=[10.0], p=[-0.3], tspan=(0.0, 10.0),
+                     save_times=ts, pdf=[(PDF_UNIFORM, 0.0, 10.0, 0.0, 1.0)]).replace(**kw)
 
 
 # ---- C3 ---------------------------------------------------------------------------------------
@@ -165,6 +199,8 @@ BUILTIN = {
     "decay1": decay1,
     "oscillator_noise": oscillator_noise,
     "gbm4": gbm4,
+    "linear2_saveat": linear2_saveat,
+    "growth_saveat": growth_saveat,
 }
 
 

@@ -19,6 +19,8 @@ DISTS = {
     "decay1": [("tn", 0.5, 1.5, 1.0, 0.1)],
     "oscillator_noise": [("tn", -4.0, 4.0, 0.0, 1.0)] * 8,
     "gbm4": [("tn", -4.0, 4.0, 0.0, 1.0)] * 8,
+    "linear2_saveat": [("u", 1.0, 10.0), ("tn", 0.0, 6.0, 3.0, 1.0)],
+    "growth_saveat": [("u", 0.0, 10.0)],
 }
 
 
@@ -51,3 +53,17 @@ def sample_points(name, n, seed=0):
         got += m
         b += 1
     return np.ascontiguousarray(np.concatenate(blocks, axis=0)) if len(blocks) > 1 else np.ascontiguousarray(blocks[0])
+
+
+def oracle_for(name, **kw):
+    """The oracle twin of a builtin product model.  The six BASELINE problems have independent C versions
+    in oracle/models_builtin.c; the time-sampled ones are compiled from the model's own dialect source
+    (the solver and the interpolant are still the oracle's own code)."""
+    import oracle
+    import scimlexpectations_jl_b200 as sme
+    spec = sme.models.builtin(name)
+    if not len(spec.save_times):
+        return oracle.OracleProblem.builtin(name, **kw)
+    return oracle.OracleProblem.from_source(spec.source, nstate=spec.nstate, nparam=spec.nparam, nx=spec.nx, nout=spec.nout,
+                                            u0=spec.u0, p=spec.p, tspan=spec.tspan, pdf=spec.pdf,
+                                            save_times=spec.save_times, **kw)

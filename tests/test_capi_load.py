@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(sme):
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/b200_expect.h but not exported"
     assert sorted(sme._capi.EXPORTS) == names
-    assert L.b200e_abi_version() == sme._capi.ABI_VERSION == 2
+    assert L.b200e_abi_version() == sme._capi.ABI_VERSION == 3
 
 
 def test_struct_layout_matches_header(sme):
@@ -31,7 +31,7 @@ def test_struct_layout_matches_header(sme):
     assert C.sizeof(sme._capi.PdfDim) == 40
     assert C.sizeof(sme._capi.Counters) == 32
     assert C.sizeof(sme._capi.CallStats) == 64
-    assert C.sizeof(sme._capi.Model) == 168
+    assert C.sizeof(sme._capi.Model) == 176
     assert C.sizeof(sme._capi.CubatureOpts) == 24 and C.sizeof(sme._capi.CubatureStats) == 88
 
 
