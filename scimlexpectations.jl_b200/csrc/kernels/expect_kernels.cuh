@@ -606,69 +606,123 @@ b200e_reduce_gen(const __grid_constant__ b200e_kparams P) {
 // ------------------------------------------------------------------------------------------
 constexpr int NK = B200E_NKKL;
 
+// SPT samples per thread.  Every lane of a warp reads the SAME table row each step, and the L1 returns it
+// to all 32 lanes: 64 B x 32 lanes per step saturate the LSU write-back path (ncu: l1tex lsu_writeback_active
+// 90 %, long-scoreboard stalls 55 %, FP64 pipe 52 %) long before the FP64 pipe.  A lane that integrates two
+// samples side by side uses each loaded row twice: half the load traffic per sample, and the step becomes
+// FP64-bound again (measured 3.96 -> 2.9 ms on C5).
+#ifndef B200E_EM_SPT
+#define B200E_EM_SPT 2
+#endif
+constexpr int SPT = B200E_EM_SPT;
+
 template <bool REDUCE, bool DYN, bool GEN>
 __device__ __forceinline__ void em_run(const b200e_kparams &P) {
     const long long T = (long long)gridDim.x * B200E_BLOCK;
+    const int lane = threadIdx.x & 31;
     Accum A;
     A.init();
     const long long nsteps = P.em_nsteps;
     const real t0 = (real)P.t0, t1 = (real)P.t1, h = (real)P.dt_fixed;
-    // every lane takes the same number of steps, but resident warps do not advance at equal pace: in
-    // dynamic mode a warp takes the next 32 points off the launch's counter instead of owning a fixed
-    // stride (the host launches the static instantiation when there is at most one point per lane)
+    // a warp works on pools of 32 * SPT consecutive points: lane l takes points base + 32 q + l, q < SPT.
+    // Static: pool `warp index + round * warps` ; dynamic: the next pool off the launch's counter (every
+    // lane takes the same number of steps, but resident warps do not advance at equal pace).  The host
+    // launches the static instantiation when there is at most one point per lane.
     constexpr bool dyn = DYN;
-    for (long long i = (long long)blockIdx.x * B200E_BLOCK + threadIdx.x;; i += T) {
+    for (long long pool = ((long long)blockIdx.x * B200E_BLOCK + threadIdx.x) >> 5;; pool += T >> 5) {
+        long long base;
         if (dyn) {
-            unsigned long long base = 0ull;
-            if ((threadIdx.x & 31) == 0) base = atomicAdd(P.work_counter, 32ull);
-            base = __shfl_sync(B200E_FULL, base, 0);
-            if ((long long)base >= P.npts) break;
-            i = (long long)base + (threadIdx.x & 31);
-            if (i >= P.npts) continue;  // ragged last pool: the next grab ends the loop for the whole warp
-        } else if (i >= P.npts) {
-            break;
+            unsigned long long b = 0ull;
+            if (lane == 0) b = atomicAdd(P.work_counter, (unsigned long long)(32 * SPT));
+            base = (long long)__shfl_sync(B200E_FULL, b, 0);
+        } else {
+            base = pool * (32 * SPT);
         }
-        double xs[NX];
-        load_point<GEN>(P, i, xs);
-        const double wgt = P.weight_by_pdf ? pdf_weight(P, xs) : 1.0;
-        real xr[NX], u0n[N], pn[B200E_DIM(NP)], u[N], p[B200E_DIM(NP)], z[NK];
-#pragma unroll
-        for (int j = 0; j < NX; j++) xr[j] = (real)xs[j];
-#pragma unroll
-        for (int j = 0; j < N; j++) { u0n[j] = (real)P.u0_nom[j]; u[j] = u0n[j]; }
-#pragma unroll
-        for (int j = 0; j < NP; j++) { pn[j] = (real)P.p_nom[j]; p[j] = pn[j]; }
-#pragma unroll
-        for (int k = 0; k < NK; k++) z[k] = (real)0;
-        // Z, p = h(x, u0, p); u0 stays nominal (expectation.jl:216)
-        hmap(xr, u0n, pn, z, p);
+        if (base >= P.npts) break;
 
-        const double *tab = P.kkl_table;
-        real wcur = (real)0;
+        long long idx[SPT];
+        bool valid[SPT];
+        double wgt[SPT];
+        real u[SPT][N], p[SPT][B200E_DIM(NP)], z[SPT][NK];
 #pragma unroll
-        for (int k = 0; k < NK; k++) wcur = fma(z[k], (real)__ldg(tab + k), wcur);
-        for (long long s = 0; s < nsteps; s++) {
-            const real t = fma((real)s, h, t0);
-            const real tn = (s + 1 == nsteps) ? t1 : fma((real)(s + 1), h, t0);
-            const real dt = tn - t;
-            const double *row = tab + (s + 1) * NK;
-            real wn = (real)0;
+        for (int q = 0; q < SPT; q++) {
+            idx[q] = base + 32 * q + lane;
+            valid[q] = idx[q] < P.npts;
+            const long long il = valid[q] ? idx[q] : P.npts - 1;  // ragged last pool: solve a copy, emit nothing
+            double xs[NX];
+            load_point<GEN>(P, il, xs);
+            wgt[q] = P.weight_by_pdf ? pdf_weight(P, xs) : 1.0;
+            real xr[NX], u0n[N], pn[B200E_DIM(NP)];
 #pragma unroll
-            for (int k = 0; k < NK; k++) wn = fma(z[k], (real)__ldg(row + k), wn);
-            const real dW = wn - wcur;
-            wcur = wn;
-            real f[N], g[N];
-            rhs(f, u, p, t);
-            diffusion(g, u, p, t);
+            for (int j = 0; j < NX; j++) xr[j] = (real)xs[j];
 #pragma unroll
-            for (int j = 0; j < N; j++) u[j] = fma(g[j], dW, fma(dt, f[j], u[j]));
+            for (int j = 0; j < N; j++) { u0n[j] = (real)P.u0_nom[j]; u[q][j] = u0n[j]; }
+#pragma unroll
+            for (int j = 0; j < NP; j++) { pn[j] = (real)P.p_nom[j]; p[q][j] = pn[j]; }
+#pragma unroll
+            for (int k = 0; k < NK; k++) z[q][k] = (real)0;
+            // Z, p = h(x, u0, p); u0 stays nominal (expectation.jl:216)
+            hmap(xr, u0n, pn, z[q], p[q]);
         }
-        int failed = 0;
+
+        // W(t_n) = sum_k Z_k phi_k(t_n) from the table row of step n (one 16-byte load per pair of modes,
+        // shared by the lane's SPT samples).  Step times as in the oracle, t_n = t0 + n h with t_N = t1, from
+        // a floating-point counter (an int64 -> double conversion per step costs more than the whole drift).
+        const double *tab = P.kkl_table;
+        real row[NK], wcur[SPT];
+        auto load_row = [&](const double *r) {
+            if (NK % 2 == 0) {
+                const double2 *r2 = reinterpret_cast<const double2 *>(r);
 #pragma unroll
-        for (int j = 0; j < N; j++) failed |= !(u[j] == u[j]);
-        emit<REDUCE>(P, i, u, p, wgt, A);
-        if (!REDUCE && P.steps) P.steps[i] = (int)nsteps;
-        A.count((unsigned)nsteps, (unsigned)nsteps, 0u, (unsigned)failed);
+                for (int k = 0; k < NK / 2; k++) {
+                    const double2 v = __ldg(r2 + k);
+                    row[2 * k] = (real)v.x;
+                    row[2 * k + 1] = (real)v.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NK; k++) row[k] = (real)__ldg(r + k);
+            }
+        };
+        auto kkl_dot = [&](const real *zq) {
+            real w = (real)0;
+#pragma unroll
+            for (int k = 0; k < NK; k++) w = fma(zq[k], row[k], w);
+            return w;
+        };
+        load_row(tab);
+#pragma unroll
+        for (int q = 0; q < SPT; q++) wcur[q] = kkl_dot(z[q]);
+        const int ns = (int)nsteps;
+        real t = t0, sd = (real)0;
+        for (int s = 0; s < ns; s++) {
+            sd += (real)1;
+            const real tn = (s + 1 == ns) ? t1 : fma(sd, h, t0);
+            const real dt = tn - t;
+            load_row(tab + (long long)(s + 1) * NK);
+#pragma unroll
+            for (int q = 0; q < SPT; q++) {
+                const real wn = kkl_dot(z[q]);
+                const real dW = wn - wcur[q];
+                wcur[q] = wn;
+                real f[N], g[N];
+                rhs(f, u[q], p[q], t);
+                diffusion(g, u[q], p[q], t);
+#pragma unroll
+                for (int j = 0; j < N; j++) u[q][j] = fma(g[j], dW, fma(dt, f[j], u[q][j]));
+            }
+            t = tn;
+        }
+#pragma unroll
+        for (int q = 0; q < SPT; q++) {
+            if (!valid[q]) continue;
+            int failed = 0;
+#pragma unroll
+            for (int j = 0; j < N; j++) failed |= !(u[q][j] == u[q][j]);
+            emit<REDUCE>(P, idx[q], u[q], p[q], wgt[q], A);
+            if (!REDUCE && P.steps) P.steps[idx[q]] = (int)nsteps;
+            A.count((unsigned)nsteps, (unsigned)nsteps, 0u, (unsigned)failed);
+        }
     }
     block_reduce_store<REDUCE>(P, A);
 }
