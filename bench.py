@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.002)
+            self._stop_evt.wait(0.005)  # a few samples per 20-step region without contending for the driver lock
 
     def stop(self):
         self._stop_evt.set()
@@ -263,14 +263,18 @@ def run_b200(args):
 
     # the path's one exchange step: all-reduce of the 2*nout sums + 4 counters (counters < 2^53 as doubles)
     red = torch.zeros(2 * nout + 4, dtype=torch.float64, device="cuda")
-    red_h = torch.zeros(2 * nout + 4, dtype=torch.float64).pin_memory()
-    red_np = red_h.numpy()
+    # two pinned staging buffers, alternated, so that a step never rewrites one an async copy may still read
+    red_hs = [torch.zeros(2 * nout + 4, dtype=torch.float64).pin_memory() for _ in range(2)]
+    red_nps = [t.numpy() for t in red_hs]
+    xstate = {"i": 0}
 
     def exchange(s, s2, c):
-        red_np[:nout] = s
-        red_np[nout:2 * nout] = s2
-        red_np[2 * nout:] = (c["nf"], c["naccept"], c["nreject"], c["nfail"])
-        red.copy_(red_h)
+        i = xstate["i"] = xstate["i"] ^ 1
+        a = red_nps[i]
+        a[:nout] = s
+        a[nout:2 * nout] = s2
+        a[2 * nout:] = (c["nf"], c["naccept"], c["nreject"], c["nfail"])
+        red.copy_(red_hs[i], non_blocking=True)
         dist.all_reduce(red)
 
     def step_resident():
