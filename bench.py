@@ -266,15 +266,18 @@ def run_b200(args):
     # two pinned staging buffers, alternated, so that a step never rewrites one an async copy may still read
     red_hs = [torch.zeros(2 * nout + 4, dtype=torch.float64).pin_memory() for _ in range(2)]
     red_nps = [t.numpy() for t in red_hs]
+    red_evs = [torch.cuda.Event() for _ in range(2)]
     xstate = {"i": 0}
 
     def exchange(s, s2, c):
         i = xstate["i"] = xstate["i"] ^ 1
+        red_evs[i].synchronize()  # the copy that last read this buffer (two steps ago) is long done
         a = red_nps[i]
         a[:nout] = s
         a[nout:2 * nout] = s2
         a[2 * nout:] = (c["nf"], c["naccept"], c["nreject"], c["nfail"])
         red.copy_(red_hs[i], non_blocking=True)
+        red_evs[i].record()
         dist.all_reduce(red)
 
     def step_resident():
