@@ -407,6 +407,47 @@ def solve(prob: ExpectationProblem, expalg, *, maxiters: int = 1000000, batch: O
     return ExpectationSolution(u, resid, res)
 
 
+def _g_powers(g: str, n: int) -> str:
+    """``g_powers(sol, p) = [g(sol, p)^i for i in 1:n]`` (reference src/expectation.jl:565-568) for a scalar
+    observable given as device source: the user's function is renamed and wrapped."""
+    if "void observable_at(" in g:
+        raise NotImplementedError("centralmoment of a time-sampled observable: take the moments per save time instead")
+    if "void observable(" not in g:
+        raise ValueError("g must define `observable(u_end, p, t_end, out)`")
+    body = "\n".join(f"    out[{i}] = out[{i - 1}] * v[0];" for i in range(1, n))
+    return (g.replace("void observable(", "void b200e_observable_base(")
+            + "B200E_FN void observable(const real* u, const real* p, real t_end, real* out) {\n"
+              "    real v[1];\n    b200e_observable_base(u, p, t_end, v);\n    out[0] = v[0];\n"
+            + body + "\n}\n")
+
+
+def centralmoment(n: int, exprob: ExpectationProblem, expalg, **kwargs):
+    """``centralmoment(n, exprob, expalg; kwargs...)`` (reference src/expectation.jl:554-593): the first ``n``
+    central moments of a scalar observable.  One solve of the n-output observable ``[g, g^2, ..., g^n]``
+    through the batched path, then the binomial expansion
+    ``mu_m = sum_k C(m,k) (-mu)^(m-k) E[X^k]`` on the host, exactly as the reference does."""
+    if n < 1:
+        raise ValueError("n must be at least 1")
+    if exprob.nout != 1:
+        raise ValueError("centralmoment needs a scalar observable (nout = 1)")
+    new = ExpectationProblem(exprob.S, _g_powers(exprob.g, n), exprob.h,
+                             None if isinstance(exprob.S, ProcessNoiseSystemMap) else exprob.d, nout=n)
+    try:
+        sol = solve(new, expalg, **kwargs)
+    finally:
+        new.close()
+    raw = np.atleast_1d(np.asarray(sol.u, dtype=np.float64))
+    mu = raw[0]
+    central = np.empty(n)
+    for m in range(1, n + 1):
+        cm = 0.0
+        for k in range(0, m + 1):
+            e_xk = 1.0 if k == 0 else raw[k - 1]
+            cm += math.comb(m, k) * (-mu) ** (m - k) * e_xk
+        central[m - 1] = cm
+    return central
+
+
 def _solve_montecarlo(prob: ExpectationProblem, alg: MonteCarlo):
     h = prob.handle()
     n = int(alg.trajectories)

@@ -540,3 +540,24 @@ def test_non_finite_inputs_are_contained(gpu):
     assert c_dirty["nfail"] == 3 and c_clean["nfail"] == 0 and c_red["nfail"] == 3
     orc = oracle.OracleProblem.builtin(name)
     assert orc.eval_nodes(bad, weight_by_pdf=False)[1]["nfail"] == 3
+
+
+def test_centralmoment_reference_testset(gpu):
+    """test/solve.jl:137-173 ("SystemMap" testset of centralmoment): du = -0.5 u, u0 ~ truncated(Normal(1, 0.1),
+    0.5, 1.5), g = sol[1, end]; Var = Var(u0) exp(-2) within 1e-3 (Koopman) / 1e-2 (MonteCarlo(10000)), first
+    central moment exactly 0 -- here through centralmoment() of the API mirror: one solve of [g, g^2] on the
+    batched device path, binomial expansion on the host."""
+    import scipy.stats as st
+    m = gpu.models
+    prob = gpu.ODEProblem(m._DECAY_RHS, [1.0], (0.0, 2.0), [])
+    smap = gpu.SystemMap(prob, gpu.Tsit5(), gpu.EnsembleB200(), save_everystep=False)
+    gd = gpu.GenericDistribution(gpu.truncated(gpu.Normal(1.0, 0.1), 0.5, 1.5))
+    ex = gpu.ExpectationProblem(smap, m.observable_components([0]), m.hmap_scatter(u0_from_x=[(0, 0)]), gd, nout=1)
+    expected_var = st.truncnorm(-5, 5, loc=1.0, scale=0.1).var() * np.exp(-2.0)
+    mk = gpu.centralmoment(2, ex, gpu.Koopman(), batch=100)
+    assert abs(mk[0]) < 1e-10 and abs(mk[1] - expected_var) < 1e-3
+    mk4 = gpu.centralmoment(4, ex, gpu.Koopman(), batch=100, quadalg=gpu.B200Cubature(), ireltol=1e-8, iabstol=1e-10)
+    assert abs(mk4[1] - expected_var) < 1e-6 and abs(mk4[2]) < 1e-6      # symmetric density: no skewness
+    mm = gpu.centralmoment(2, ex, gpu.MonteCarlo(10000, seed=1))
+    assert abs(mm[0]) < 1e-10 and abs(mm[1] - expected_var) < 1e-2
+    ex.close()
