@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B200E_ABI_VERSION 3
+#define B200E_ABI_VERSION 4
 
 /* limits (compile-time dims of the generated kernel) */
 #define B200E_MAX_STATE 16
@@ -70,14 +70,20 @@ enum { B200E_LAYOUT_POINT_MAJOR = 0, B200E_LAYOUT_SOA = 1 };
  * run-time assignment (differences ~1e-16 relative).  STATIC: lane l owns points l, l+T, l+2T, ...;
  * sums are bit-reproducible for a given launch shape. */
 enum { B200E_SCHED_DYNAMIC = 0, B200E_SCHED_STATIC = 1 };
-enum { B200E_PDF_NONE = 0, B200E_PDF_UNIFORM = 1, B200E_PDF_NORMAL = 2, B200E_PDF_TRUNCNORMAL = 3 };
+enum { B200E_PDF_NONE = 0, B200E_PDF_UNIFORM = 1, B200E_PDF_NORMAL = 2, B200E_PDF_TRUNCNORMAL = 3, B200E_PDF_TABLE = 4 };
 
 /* one factor of GenericDistribution(dists...) (src/distribution_utils.jl:40-48) */
 typedef struct {
     int32_t kind; /* B200E_PDF_* */
     int32_t _pad;
-    double lo, hi;    /* support: uniform bounds / truncation bounds (+-inf for plain normal) */
+    double lo, hi;    /* support: uniform bounds / truncation bounds (+-inf for plain normal) / table grid ends */
     double mu, sigma; /* normal parameters */
+    /* B200E_PDF_TABLE: density values on the uniform grid lo + i (hi - lo) / (ntable - 1), interpolated
+     * linearly, 0 outside [lo, hi] -- pdf(kde, x) of a KernelDensity estimate
+     * (docs/src/tutorials/gpu_bayesian.md:153-166: pdf_func(x) = prod(pdf.(p_kde, x)), lb / ub = the grid ends).
+     * Koopman only: a tabulated factor cannot be sampled.  The values are copied at b200e_create. */
+    const double *table;
+    int64_t ntable;
 } b200e_pdf_dim;
 
 /*

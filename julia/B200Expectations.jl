@@ -27,6 +27,7 @@ const LIB = get(ENV, "B200E_LIB", "libb200expect.so")
 struct PdfDim            # b200e_pdf_dim
     kind::Int32; _pad::Int32
     lo::Float64; hi::Float64; mu::Float64; sigma::Float64
+    table::Ptr{Float64}; ntable::Int64       # kind 4: density values on the uniform grid lo .. hi (copied by b200e_create)
 end
 struct CModel            # b200e_model (field order = include/b200_expect.h)
     struct_size::UInt32
@@ -63,9 +64,11 @@ Base.@kwdef struct EnsembleB200 <: SciMLBase.EnsembleAlgorithm
     seed::UInt64 = 0x0000000000000000
 end
 
-pdfdim(d::Uniform) = PdfDim(1, 0, minimum(d), maximum(d), 0.0, 1.0)
-pdfdim(d::Normal) = PdfDim(2, 0, -Inf, Inf, mean(d), std(d))
-pdfdim(d::Truncated{<:Normal}) = PdfDim(3, 0, minimum(d), maximum(d), mean(d.untruncated), std(d.untruncated))
+pdfdim(d::Uniform) = PdfDim(1, 0, minimum(d), maximum(d), 0.0, 1.0, C_NULL, 0)
+pdfdim(d::Normal) = PdfDim(2, 0, -Inf, Inf, mean(d), std(d), C_NULL, 0)
+pdfdim(d::Truncated{<:Normal}) = PdfDim(3, 0, minimum(d), maximum(d), mean(d.untruncated), std(d.untruncated), C_NULL, 0)
+# a KernelDensity.UnivariateKDE (gpu_bayesian.md:153-166); `k.density` must stay alive until b200e_create returns
+pdfdim(k::KernelDensity.UnivariateKDE) = PdfDim(4, 0, first(k.x), last(k.x), 0.0, 1.0, pointer(k.density), length(k.density))
 pdfdim(d) = error("B200Expectations: no device pdf table for $(typeof(d)); supported: Uniform, Normal, truncated(Normal)")
 
 check(rc, h) = rc == 0 ? nothing :

@@ -33,7 +33,7 @@ OBS_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_dou
 
 class PdfDim(C.Structure):
     _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("lo", C.c_double), ("hi", C.c_double),
-                ("mu", C.c_double), ("sigma", C.c_double)]
+                ("mu", C.c_double), ("sigma", C.c_double), ("table", C.POINTER(C.c_double)), ("ntable", C.c_int64)]
 
 
 class Problem(C.Structure):
@@ -151,10 +151,15 @@ class OracleProblem:
         return self
 
     def set_pdf(self, dims):
-        """dims: list of (kind, lo, hi, mu, sigma)"""
+        """dims: list of (kind, lo, hi, mu, sigma[, table values])"""
         arr = (PdfDim * len(dims))()
-        for a, (kind, lo, hi, mu, sigma) in zip(arr, dims):
+        for a, d in zip(arr, dims):
+            kind, lo, hi, mu, sigma = d[:5]
             a.kind, a.lo, a.hi, a.mu, a.sigma = int(kind), float(lo), float(hi), float(mu), float(sigma)
+            if int(kind) == 4:  # tabulated density: (4, lo, hi, 0, 1, values)
+                tab = np.ascontiguousarray(d[5], dtype=np.float64)
+                self._keep.append(tab)
+                a.table, a.ntable = tab.ctypes.data_as(C.POINTER(C.c_double)), len(tab)
         self._keep.append(arr)
         self.st.pdf = C.cast(arr, C.POINTER(PdfDim))
 

@@ -82,6 +82,14 @@ static double logpdf_1d(const orc_pdf_dim *d, double x) {
         double z = (x - d->mu) / d->sigma;
         return -0.5 * z * z - log(d->sigma) - half_log_2pi;
     }
+    case ORC_PDF_TABLE: {
+        if (!(x >= d->lo && x <= d->hi)) return -INFINITY;
+        double g = (x - d->lo) * ((double)(d->ntable - 1) / (d->hi - d->lo));
+        int64_t i = (int64_t)g;
+        if (i > d->ntable - 2) i = d->ntable - 2;
+        double v = d->table[i] + (g - (double)i) * (d->table[i + 1] - d->table[i]);
+        return v > 0 ? log(v) : -INFINITY;
+    }
     case ORC_PDF_TRUNCNORMAL: {
         if (!(x >= d->lo && x <= d->hi)) return -INFINITY;
         double z = (x - d->mu) / d->sigma;

@@ -46,7 +46,7 @@ typedef void (*orc_obs_fn)(const double *u_end, const double *p, double t_end, d
  * interpolated state; writes the nout / nsave outputs of slot k */
 typedef void (*orc_obs_at_fn)(int k, double t_k, const double *u_k, const double *p, double *out_k);
 
-enum { ORC_PDF_NONE = 0, ORC_PDF_UNIFORM = 1, ORC_PDF_NORMAL = 2, ORC_PDF_TRUNCNORMAL = 3 };
+enum { ORC_PDF_NONE = 0, ORC_PDF_UNIFORM = 1, ORC_PDF_NORMAL = 2, ORC_PDF_TRUNCNORMAL = 3, ORC_PDF_TABLE = 4 };
 
 /* one factor of GenericDistribution(dists...), reference distribution_utils.jl:40-48 */
 typedef struct {
@@ -54,6 +54,10 @@ typedef struct {
     int32_t _pad;
     double lo, hi;    /* support (uniform bounds / truncation bounds); +-inf for normal */
     double mu, sigma; /* normal parameters (unused for uniform) */
+    /* ORC_PDF_TABLE: pdf(kde, x) of a KernelDensity estimate (docs/src/tutorials/gpu_bayesian.md:153-166):
+     * ntable values on the uniform grid lo .. hi, linear interpolation, 0 outside */
+    const double *table;
+    int64_t ntable;
 } orc_pdf_dim;
 
 enum { ORC_SOLVER_TSIT5 = 0, ORC_SOLVER_EM = 1 };

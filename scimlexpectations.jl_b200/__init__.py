@@ -8,7 +8,8 @@ from ._capi import (B200Error, DeviceArray, Handle, ModelSpec, PinnedArray, comp
                     load_library, measure_fma_peak)
 from .api import (EM, B200Cubature, BatchIntegralFunction, CubatureJLh, EnsembleB200, ExpectationProblem,  # noqa: F401
                   ExpectationSolution, GenericDistribution, Koopman, MonteCarlo, Normal, ODEProblem,
-                  ProcessNoiseSystemMap, SDEProblem, SystemMap, Truncated, Tsit5, Uniform, build_integrand, centralmoment,
+                  ProcessNoiseSystemMap, SDEProblem, SystemMap, Truncated, Tsit5, Uniform, UnivariateKDE, build_integrand,
+                  centralmoment,
                   extrema, maximum, minimum, pdf, rand, solve, truncated)
 from .cubature import hcubature_v  # noqa: F401
 

@@ -17,13 +17,13 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libb200expect.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_STATE, MAX_PARAM, MAX_X, MAX_OUT, MAX_KKL, MAX_SAVE = 16, 32, 32, 64, 32, 64
 OK, ERR_INVALID, ERR_COMPILE, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
 SOLVER_TSIT5, SOLVER_EM = 0, 1
 FP64, FP32 = 0, 1
 LAYOUT_POINT_MAJOR, LAYOUT_SOA = 0, 1
-PDF_NONE, PDF_UNIFORM, PDF_NORMAL, PDF_TRUNCNORMAL = 0, 1, 2, 3
+PDF_NONE, PDF_UNIFORM, PDF_NORMAL, PDF_TRUNCNORMAL, PDF_TABLE = 0, 1, 2, 3, 4
 SCHED_DYNAMIC, SCHED_STATIC = 0, 1
 
 _ERR_NAMES = {ERR_INVALID: "B200E_ERR_INVALID", ERR_COMPILE: "B200E_ERR_COMPILE", ERR_CUDA: "B200E_ERR_CUDA",
@@ -50,7 +50,7 @@ class B200Error(RuntimeError):
 
 class PdfDim(C.Structure):
     _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("lo", C.c_double), ("hi", C.c_double),
-                ("mu", C.c_double), ("sigma", C.c_double)]
+                ("mu", C.c_double), ("sigma", C.c_double), ("table", C.POINTER(C.c_double)), ("ntable", C.c_int64)]
 
 
 class Model(C.Structure):
@@ -195,7 +195,7 @@ class ModelSpec:
     dtmax: float = 0.0
     dt_fixed: float = 0.0
     maxiters: int = 100000
-    pdf: Optional[Sequence[tuple]] = None  # [(kind, lo, hi, mu, sigma)] * nx
+    pdf: Optional[Sequence[tuple]] = None  # [(kind, lo, hi, mu, sigma[, table values for PDF_TABLE])] * nx
     devices: Optional[Sequence[int]] = None
     block_size: int = 0
     blocks_per_sm: int = 0
@@ -230,9 +230,13 @@ class ModelSpec:
         m.maxiters = int(self.maxiters)
         if self.pdf is not None:
             arr = (PdfDim * len(self.pdf))()
-            for a, (kind, lo, hi, mu, sigma) in zip(arr, self.pdf):
+            for a, d in zip(arr, self.pdf):
+                kind, lo, hi, mu, sigma = d[:5]
                 a.kind, a.lo, a.hi, a.mu, a.sigma = int(kind), float(lo), float(hi), float(mu), float(sigma)
-            keep.append(arr)
+                if int(kind) == PDF_TABLE:  # (PDF_TABLE, lo, hi, 0, 1, values): tabulated density on a uniform grid
+                    tab = np.ascontiguousarray(d[5], dtype=np.float64)
+                    keep.append(tab)
+                    a.table, a.ntable = tab.ctypes.data_as(C.POINTER(C.c_double)), len(tab)
             m.pdf = C.cast(arr, C.POINTER(PdfDim))
         if self.devices is not None:
             devs = (C.c_int32 * len(self.devices))(*[int(d) for d in self.devices])

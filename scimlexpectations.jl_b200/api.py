@@ -30,7 +30,8 @@ import numpy as np
 from scipy.special import ndtr, ndtri
 
 from . import _capi
-from ._capi import FP32, FP64, LAYOUT_POINT_MAJOR, ModelSpec, PDF_NONE, PDF_NORMAL, PDF_TRUNCNORMAL, PDF_UNIFORM
+from ._capi import (FP32, FP64, LAYOUT_POINT_MAJOR, ModelSpec, PDF_NONE, PDF_NORMAL, PDF_TABLE, PDF_TRUNCNORMAL,
+                    PDF_UNIFORM)
 from .cubature import CubatureResult, hcubature_v
 
 # ---------------------------------------------------------------------------------------------
@@ -92,6 +93,52 @@ class Truncated:
 
     def table(self):
         return (PDF_TRUNCNORMAL, self.lower, self.upper, self.untruncated.mu, self.untruncated.sigma)
+
+
+class UnivariateKDE:
+    """A density tabulated on a uniform grid -- what ``kde(samples)`` of KernelDensity.jl returns (fields ``x``,
+    ``density``) and what ``pdf(kde, x)`` interpolates (docs/src/tutorials/gpu_bayesian.md:153-166:
+    ``pdf_func(x) = prod(pdf.(p_kde, x))``, ``lb / ub`` = the grid ends).  Linear interpolation between grid
+    points, 0 outside.  Koopman only (``rand_func() = nothing`` in the tutorial): it cannot be sampled."""
+
+    def __init__(self, x, density):
+        self.x = np.ascontiguousarray(x, dtype=np.float64)
+        self.density = np.ascontiguousarray(density, dtype=np.float64)
+        if self.x.ndim != 1 or self.x.shape != self.density.shape or len(self.x) < 2:
+            raise ValueError("x and density must be 1-D arrays of equal length >= 2")
+        if not np.allclose(np.diff(self.x), (self.x[-1] - self.x[0]) / (len(self.x) - 1), rtol=1e-9, atol=0):
+            raise ValueError("the grid must be uniform")
+
+    @classmethod
+    def from_samples(cls, samples, npoints: int = 2048, bandwidth: Optional[float] = None):
+        """Gaussian KDE on ``npoints`` grid points with Silverman's rule and a 4-bandwidth margin (the defaults
+        of KernelDensity.jl's ``kde``)."""
+        v = np.asarray(samples, dtype=np.float64).ravel()
+        if bandwidth is None:
+            q75, q25 = np.percentile(v, [75, 25])
+            width = min(v.std(ddof=1), (q75 - q25) / 1.34)
+            bandwidth = 0.9 * width * len(v) ** (-0.2)
+        lo, hi = v.min() - 4.0 * bandwidth, v.max() + 4.0 * bandwidth
+        x = np.linspace(lo, hi, npoints)
+        z = (x[:, None] - v[None, :]) / bandwidth
+        dens = np.exp(-0.5 * z * z).sum(axis=1) / (len(v) * bandwidth * math.sqrt(2.0 * math.pi))
+        return cls(x, dens)
+
+    def minimum(self): return float(self.x[0])
+    def maximum(self): return float(self.x[-1])
+
+    def pdf(self, x):
+        return float(np.interp(x, self.x, self.density, left=0.0, right=0.0))
+
+    def logpdf(self, x):
+        v = self.pdf(x)
+        return math.log(v) if v > 0 else -math.inf
+
+    def icdf(self, u):
+        raise NotImplementedError("a tabulated density cannot be sampled (Koopman only)")
+
+    def table(self):
+        return (PDF_TABLE, float(self.x[0]), float(self.x[-1]), 0.0, 1.0, self.density)
 
 
 def truncated(d: Normal, lower: float, upper: float) -> Truncated:

@@ -17,8 +17,10 @@
 struct b200e_kpdf {
     double lo, hi, mu, inv_sigma, logc;
     double smp_a, smp_b, smp_c, smp_d;
+    const double *tab;   // kind 4: density table on the uniform grid lo + i / inv_dx (device memory), ntab entries
+    double inv_dx;
     int kind;
-    int _pad;
+    int ntab;
 };
 
 struct b200e_kparams {

@@ -33,19 +33,32 @@ __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0
 
 // pdf(d, x) = exp(sum_j logpdf(d_j, x_j))   (src/distribution_utils.jl:42, one exp for the product)
 __device__ __forceinline__ double pdf_weight(const b200e_kparams &P, const double *xs) {
-    double s = 0.0;
+    double s = 0.0, tabulated = 1.0;
 #pragma unroll
     for (int j = 0; j < NX; j++) {
         const int kind = P.pdf[j].kind;
         if (kind != 0) {
             const double xj = xs[j];
             const bool inside = (xj >= P.pdf[j].lo) && (xj <= P.pdf[j].hi);
-            const double z = (xj - P.pdf[j].mu) * P.pdf[j].inv_sigma;
-            const double lp = fma(-0.5 * z, z, P.pdf[j].logc);
-            s += inside ? lp : neg_inf();
+            if (B200E_TABLE_PDF && kind == 4) {  // compiled in only when the model has a tabulated factor
+                // tabulated factor (a KDE): linear interpolation on the uniform grid, 0 outside
+                double v = 0.0;
+                if (inside) {
+                    const double g = (xj - P.pdf[j].lo) * P.pdf[j].inv_dx;
+                    int i = (int)g;
+                    i = i < P.pdf[j].ntab - 2 ? i : P.pdf[j].ntab - 2;
+                    const double a = __ldg(P.pdf[j].tab + i), b = __ldg(P.pdf[j].tab + i + 1);
+                    v = fma(g - (double)i, b - a, a);
+                }
+                tabulated *= v;
+            } else {
+                const double z = (xj - P.pdf[j].mu) * P.pdf[j].inv_sigma;
+                const double lp = fma(-0.5 * z, z, P.pdf[j].logc);
+                s += inside ? lp : neg_inf();
+            }
         }
     }
-    return exp(s);
+    return exp(s) * tabulated;
 }
 
 // GEN: the point is not loaded but drawn -- rand(d) of the MonteCarlo prob_func (expectation.jl:278) --

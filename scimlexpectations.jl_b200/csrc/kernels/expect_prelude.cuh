@@ -5,6 +5,8 @@
 //   #define B200E_FP32     0 | 1
 //   #define B200E_BLOCK    threads per block,  B200E_MINBLOCKS  resident blocks per SM
 //   #define B200E_CLIP_DTMAX  1 when the model sets dtmax < t1 - t0
+//   #define B200E_NSAVE    number of save times of a time-sampled observable (0: end-state observable)
+//   #define B200E_TABLE_PDF   1 when a factor of the density is tabulated
 // and the text of b200e_kparams.h.
 //
 // Dialect of the model source (valid as CUDA device code here and as C in the test oracle):

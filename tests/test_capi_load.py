@@ -23,12 +23,12 @@ def test_library_exports_every_declared_symbol(sme):
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/b200_expect.h but not exported"
     assert sorted(sme._capi.EXPORTS) == names
-    assert L.b200e_abi_version() == sme._capi.ABI_VERSION == 3
+    assert L.b200e_abi_version() == sme._capi.ABI_VERSION == 4
 
 
 def test_struct_layout_matches_header(sme):
     # sizes computed by hand from the header (LP64): catches drift between the ctypes mirror and the C structs
-    assert C.sizeof(sme._capi.PdfDim) == 40
+    assert C.sizeof(sme._capi.PdfDim) == 56
     assert C.sizeof(sme._capi.Counters) == 32
     assert C.sizeof(sme._capi.CallStats) == 64
     assert C.sizeof(sme._capi.Model) == 176
