@@ -192,6 +192,18 @@ def gbm4(**kw) -> ModelSpec:
                      pdf=list(_KKL8_PDF)).replace(**kw)
 
 
+# ---- a larger state: radioactive-decay chain u_0 -> u_1 -> ... -> u_7 with uncertain rates (synthetic; exercises
+# the register budget: 8 states x 7 stages do not fit 128 registers) ----
+def decay_chain8(**kw) -> ModelSpec:
+    n = 8
+    lines = ["    du[0] = -p[0] * u[0];"] + [f"    du[{i}] = p[{i - 1}] * u[{i - 1}] - p[{i}] * u[{i}];" for i in range(1, n)]
+    rhs = "B200E_FN void rhs(real* du, const real* u, const real* p, real t) {\n" + "\n".join(lines) + "\n}\n"
+    src = rhs + hmap_scatter(p_from_x=[(i, i) for i in range(n)]) + observable_components(list(range(n)))
+    return ModelSpec(source=src, nstate=n, nparam=n, nx=n, nout=n, u0=[1.0] + [0.0] * (n - 1), p=[1.0] * n,
+                     tspan=(0.0, 2.0),
+                     pdf=[(PDF_UNIFORM, 0.5 + 0.1 * i, 1.5 + 0.1 * i, 0.0, 1.0) for i in range(n)]).replace(**kw)
+
+
 BUILTIN = {
     "linear2": linear2,
     "lotka_volterra": lotka_volterra,
@@ -201,6 +213,7 @@ BUILTIN = {
     "gbm4": gbm4,
     "linear2_saveat": linear2_saveat,
     "growth_saveat": growth_saveat,
+    "decay_chain8": decay_chain8,
 }
 
 

@@ -21,6 +21,7 @@ DISTS = {
     "gbm4": [("tn", -4.0, 4.0, 0.0, 1.0)] * 8,
     "linear2_saveat": [("u", 1.0, 10.0), ("tn", 0.0, 6.0, 3.0, 1.0)],
     "growth_saveat": [("u", 0.0, 10.0)],
+    "decay_chain8": [("u", 0.5 + 0.1 * i, 1.5 + 0.1 * i) for i in range(8)],
 }
 
 
@@ -57,12 +58,12 @@ def sample_points(name, n, seed=0):
 
 def oracle_for(name, **kw):
     """The oracle twin of a builtin product model.  The six BASELINE problems have independent C versions
-    in oracle/models_builtin.c; the time-sampled ones are compiled from the model's own dialect source
+    in oracle/models_builtin.c; the others (time-sampled observables, decay_chain8) are compiled from the model's own dialect source
     (the solver and the interpolant are still the oracle's own code)."""
     import oracle
     import scimlexpectations_jl_b200 as sme
     spec = sme.models.builtin(name)
-    if not len(spec.save_times):
+    if not len(spec.save_times) and name in ("linear2", "lotka_volterra", "lorenz63", "decay1", "oscillator_noise", "gbm4"):
         return oracle.OracleProblem.builtin(name, **kw)
     return oracle.OracleProblem.from_source(spec.source, nstate=spec.nstate, nparam=spec.nparam, nx=spec.nx, nout=spec.nout,
                                             u0=spec.u0, p=spec.p, tspan=spec.tspan, pdf=spec.pdf,

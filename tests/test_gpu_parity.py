@@ -561,3 +561,29 @@ def test_centralmoment_reference_testset(gpu):
     mm = gpu.centralmoment(2, ex, gpu.MonteCarlo(10000, seed=1))
     assert abs(mm[0]) < 1e-10 and abs(mm[1] - expected_var) < 1e-2
     ex.close()
+
+
+def test_larger_state_dimension(gpu):
+    """8 states (a decay chain with 8 uncertain rates): 8 x 7 stage values do not fit the 128 registers of two
+    resident blocks; the kernel spills a few words into L1 (measured faster than one block of 255 registers).
+    Same parity bars, plus the closed form of the first two species."""
+    from tests.sampling_util import oracle_for
+    name = "decay_chain8"
+    x = sample_points(name, 30000, seed=41)
+    orc = oracle_for(name)
+    ref, cref, sref = orc.eval_nodes(x, weight_by_pdf=True, want_steps=True)
+    so, s2o, co = orc.reduce_samples(x)
+    with gpu.Handle(gpu.models.builtin(name)) as h:
+        dx, steps = h.eval_nodes(x, weight_by_pdf=True, want_steps=True)
+        c = h.last_counters()
+        st = h.last_stats()
+        s, s2, cr = h.reduce_samples(x)
+        raw = h.eval_nodes(x, weight_by_pdf=False)
+    assert c == cref == cr and np.array_equal(steps, sref)
+    assert st["regs_per_thread"] == 128 and st["blocks_per_sm_occ"] == 2
+    med, mx = _node_err(dx, ref)
+    assert med <= 1e-10 and mx <= 2e-6
+    assert np.max(np.abs(s - so) / np.abs(so)) < 1e-8
+    k0, k1 = x[:, 0], x[:, 1]
+    assert np.allclose(raw[:, 0], np.exp(-2.0 * k0), rtol=2e-3)
+    assert np.allclose(raw[:, 1], k0 / (k1 - k0) * (np.exp(-2.0 * k0) - np.exp(-2.0 * k1)), rtol=5e-3, atol=1e-5)
