@@ -195,3 +195,24 @@ def test_oracle_layouts_threads_and_edge_cases():
     xs = sample_points("lotka_volterra", 10, seed=1)
     d, c = short.eval_nodes(xs, weight_by_pdf=False)
     assert c["nfail"] == 10 and c["naccept"] + c["nreject"] == 50 and np.all(np.isfinite(d))
+
+
+def test_nonlinear_models_converge_to_an_independent_integrator():
+    """Lotka-Volterra and Lorenz have no reference fixture: the oracle at tight tolerances must
+    converge to the solution scipy's DOP853 (a different method, a different code base) finds, and at the
+    DEFAULT tolerances its global error must sit at the level those tolerances imply."""
+    from scipy.integrate import solve_ivp
+    lv = lambda t, u, p: [(p[0] - p[1] * u[1]) * u[0], (p[3] * u[0] - p[2]) * u[1]]
+    lz = lambda t, u, p: [p[0] * (u[1] - u[0]), u[0] * (p[1] - u[2]) - u[1], u[0] * u[1] - p[2] * u[2]]
+    for name, f, t1 in (("lotka_volterra", lv, 10.0), ("lorenz63", lz, 1.0)):
+        x = sample_points(name, 12, seed=17)
+        tight, _ = oracle.OracleProblem.builtin(name, abstol=1e-12, reltol=1e-12).eval_nodes(x, weight_by_pdf=False)
+        loose, _ = oracle.OracleProblem.builtin(name).eval_nodes(x, weight_by_pdf=False)
+        for i, xi in enumerate(x):
+            if name == "lotka_volterra":
+                u0, p, pick = [1.0, 1.0], xi, [0]
+            else:
+                u0, p, pick = xi[3:], xi[:3], [0, 1, 2]
+            ref = solve_ivp(f, (0.0, t1), u0, method="DOP853", args=(p,), rtol=1e-13, atol=1e-13).y[pick, -1]
+            assert np.max(np.abs(tight[i] - ref) / (1e-3 + np.abs(ref))) < 2e-9, (name, i)
+            assert np.max(np.abs(loose[i] - ref) / (1e-3 + np.abs(ref))) < 1e-1, (name, i)   # reltol 1e-3 over ~2 LV periods
