@@ -448,13 +448,16 @@ def test_single_process_multi_device_sharding(gpu):
     with gpu.Handle(gpu.models.builtin(name, devices=[0])) as h:
         s1, q1, c1 = h.reduce_samples(x)
         d1 = h.eval_nodes(x)
+        sg1, qg1, cg1 = h.reduce_generated(3, 300007, first_index=77)
     devs = list(range(min(nd, 8)))
     with gpu.Handle(gpu.models.builtin(name, devices=devs, chunk_points=50000)) as h:
         s, q, c = h.reduce_samples(x)
         d = h.eval_nodes(x)
         cn = h.last_counters()
-    assert c == c1 and cn == c1
+        sg, qg, cg = h.reduce_generated(3, 300007, first_index=77)   # every device draws its own index range
+    assert c == c1 and cn == c1 and cg == cg1
     assert np.allclose(s, s1, rtol=1e-12) and np.allclose(q, q1, rtol=1e-12)
+    assert np.allclose(sg, sg1, rtol=1e-12) and np.allclose(qg, qg1, rtol=1e-12)
     assert np.array_equal(d, d1)
 
 
