@@ -174,7 +174,9 @@ def test_static_schedule_is_bit_reproducible_and_dynamic_agrees(gpu):
             s_a, q_a, c_a = h.reduce_samples(x)
             s_b, q_b, c_b = h.reduce_samples(x)
             nodes_static, steps_static = h.eval_nodes(x, want_steps=True)
+            g_a, g_b = h.reduce_generated(8, n), h.reduce_generated(8, n)     # the sampled kernel follows the schedule too
         assert np.array_equal(s_a, s_b) and np.array_equal(q_a, q_b) and c_a == c_b
+        assert np.array_equal(g_a[0], g_b[0]) and np.array_equal(g_a[1], g_b[1]) and g_a[2] == g_b[2]
         with gpu.Handle(gpu.models.builtin(name, **shape)) as h:
             s_d, q_d, c_d = h.reduce_samples(x)
             assert h.last_stats()["grid"] * 32 < n
