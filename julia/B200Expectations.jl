@@ -40,7 +40,7 @@ struct CModel            # b200e_model (field order = include/b200_expect.h)
     pdf::Ptr{PdfDim}
     n_devices::Int32; devices::Ptr{Int32}
     block_size::Int32; blocks_per_sm::Int32; refill_threshold::Int32; chunk_points::Int32
-    schedule::Int32                     # 0 dynamic (default), 1 static = bit-reproducible sums
+    schedule::Int32                     # 0 dynamic (default), 1 static, 2 dynamic + reproducible (B200E_SCHED_*)
     nsave::Int32; save_times::Ptr{Float64}   # time-sampled observables (saveat / sol(t)): nout = nsave * outputs per time
     cache_dir::Cstring
 end
@@ -58,7 +58,7 @@ Base.@kwdef struct EnsembleB200 <: SciMLBase.EnsembleAlgorithm
     model::B200Model
     devices::Vector{Int32} = Int32[]           # empty: current device; several: sharded + one NCCL all-reduce
     fp32::Bool = false
-    schedule::Int32 = 0                        # 0 dynamic work distribution, 1 static (bit-reproducible sums)
+    schedule::Int32 = 0                        # 0 dynamic work distribution, 1 static, 2 dynamic with bit-reproducible sums
     sampler::Symbol = :device                  # MonteCarlo: :device draws rand(d) in the kernel (counter-based
                                                # stream, reproducible by b200e_sample_host); :host ships rand(d)
     seed::UInt64 = 0x0000000000000000

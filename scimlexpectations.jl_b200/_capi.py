@@ -24,7 +24,7 @@ SOLVER_TSIT5, SOLVER_EM = 0, 1
 FP64, FP32 = 0, 1
 LAYOUT_POINT_MAJOR, LAYOUT_SOA = 0, 1
 PDF_NONE, PDF_UNIFORM, PDF_NORMAL, PDF_TRUNCNORMAL, PDF_TABLE = 0, 1, 2, 3, 4
-SCHED_DYNAMIC, SCHED_STATIC = 0, 1
+SCHED_DYNAMIC, SCHED_STATIC, SCHED_DYNAMIC_REPRODUCIBLE = 0, 1, 2
 
 _ERR_NAMES = {ERR_INVALID: "B200E_ERR_INVALID", ERR_COMPILE: "B200E_ERR_COMPILE", ERR_CUDA: "B200E_ERR_CUDA",
               ERR_NO_DEVICE: "B200E_ERR_NO_DEVICE", ERR_NOMEM: "B200E_ERR_NOMEM", ERR_NCCL: "B200E_ERR_NCCL"}

@@ -234,7 +234,7 @@ class EnsembleB200:
     blocks_per_sm: int = 0
     refill_threshold: int = 0
     chunk_points: int = 0
-    schedule: int = 0   # 0 dynamic work distribution (default), 1 static = bit-reproducible sums
+    schedule: int = 0   # 0 dynamic work distribution (default), 1 static, 2 dynamic with bit-reproducible sums
 
 
 class SystemMap:

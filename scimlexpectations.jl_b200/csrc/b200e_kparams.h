@@ -34,6 +34,8 @@ struct b200e_kparams {
                                        // launches: the last block to finish resets them
     double *final_sums;                // optional [2*nout]: the last block folds all per-block partials of the launch
     unsigned long long *final_counts;  // optional [4]: same for the counters
+    double *chunk_rows;                // reproducible dynamic schedule: [rows][2*nout] sums, one row per super-chunk
+    long long super_chunks;            //   chunks of 32 consecutive points per super-chunk
     const double *kkl_table;  // EM: [nsteps+1][n_kkl] basis values sqrt(2) sin((k-1/2) pi t_n)/((k-1/2) pi)
     long long npts;         // points in this launch
     long long ld;           // SoA leading dimension of x and dx (total points of the caller's array)

@@ -526,10 +526,28 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
 
     bool more = dyn;  // dynamic mode, warp-uniform: the launch still has unassigned points
     const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
+
+    // Reproducible dynamic schedule (B200E_SCHED_DYNAMIC_REPRODUCIBLE): the warp takes SUPER-CHUNKS of
+    // P.super_chunks x 32 consecutive points off the counter, starts 32 trajectories at a time, sums every
+    // finished chunk over its lanes with a fixed shuffle tree, adds the chunk sums in chunk order, and
+    // writes ONE row of sums per super-chunk.  A row is a function of the points of its super-chunk only
+    // and the rows are folded in index order afterwards: the result does not depend on which warp solved
+    // what, nor on the launch shape.
+    constexpr bool repro = B200E_REPRO && REDUCE && DYN && B200E_NSAVE == 0;
+    __shared__ double sh_wacc[repro ? NWARPS : 1][repro ? NACC : 1];
+    long long sc_next = 0, sc_row = -1;
+    int sc_left = 0;
+    if (repro) {
+        thr_eff = 32;
+        tune = false;
+        if ((threadIdx.x & 31) < NACC) sh_wacc[threadIdx.x >> 5][threadIdx.x & 31] = 0.0;
+        for (int k = 32 + (threadIdx.x & 31); k < NACC; k += 32) sh_wacc[threadIdx.x >> 5][k] = 0.0;
+        __syncwarp();
+    }
     for (;;) {
         // ---- refill phase: runs only when the set of stepping lanes has changed ----
         const bool wants = (L.state == LANE_DONE) ||
-                           (L.state == LANE_EMPTY && (dyn ? more : next < P.npts));
+                           (L.state == LANE_EMPTY && (dyn ? (more || (repro && sc_left > 0)) : next < P.npts));
         const unsigned idle_m = __ballot_sync(B200E_FULL, wants);
         unsigned act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
         if ((idle_m | act_m) == 0u) break;
@@ -543,17 +561,70 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 if (mx * 128u > sm * 5u) thr_eff = 8;  // max > 1.25 * mean
                 tune = false;
             }
+#if B200E_NSAVE == 0
+            if (repro && done_m != 0u) {
+                // chunk sum in a fixed order: lanes without a point contribute zeros
+                real out[NOUT];
+#pragma unroll
+                for (int k = 0; k < NOUT; k++) out[k] = R_(0.0);
+                if (L.state == LANE_DONE) observable(L.u, L.p, (real)P.t1, out);
+#pragma unroll 1
+                for (int k = 0; k < NOUT; k++) {
+                    double v = (L.state == LANE_DONE) ? (double)out[k] : 0.0;
+                    if (P.weight_by_pdf) v *= wgt;
+                    double v2 = v * v;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        v += __shfl_xor_sync(B200E_FULL, v, off);
+                        v2 += __shfl_xor_sync(B200E_FULL, v2, off);
+                    }
+                    if ((threadIdx.x & 31) == 0) {
+                        sh_wacc[threadIdx.x >> 5][k] += v;
+                        sh_wacc[threadIdx.x >> 5][NOUT + k] += v2;
+                    }
+                }
+            }
+#endif
             if (L.state == LANE_DONE) {
 #if B200E_NSAVE > 0
                 emit_missing<REDUCE>(P, cur, L.ksave, wgt, A);
 #else
-                emit<REDUCE>(P, cur, L.u, L.p, wgt, A);
+                if (!repro) emit<REDUCE>(P, cur, L.u, L.p, wgt, A);
 #endif
                 if (!REDUCE && P.steps) P.steps[cur] = (int)(L.nacc + L.nrej);
                 A.count(L.nf0 + 6u * (L.nacc + L.nrej), L.nacc, L.nrej, L.failed ? 1u : 0u);
                 L.state = LANE_EMPTY;
             }
-            if (dyn) {
+            if (repro) {
+                if (sc_left == 0 && sc_row >= 0) {  // the super-chunk is complete: its row leaves the warp
+                    __syncwarp();
+                    for (int k = threadIdx.x & 31; k < NACC; k += 32) {
+                        P.chunk_rows[sc_row * NACC + k] = sh_wacc[threadIdx.x >> 5][k];
+                        sh_wacc[threadIdx.x >> 5][k] = 0.0;
+                    }
+                    __syncwarp();
+                    sc_row = -1;
+                }
+                next = P.npts;
+                if (sc_left == 0 && more) {
+                    const long long span = (long long)P.super_chunks * 32;
+                    unsigned long long base = 0ull;
+                    if ((threadIdx.x & 31) == 0) base = atomicAdd(P.work_counter, (unsigned long long)span);
+                    base = __shfl_sync(B200E_FULL, base, 0);
+                    more = (long long)base + span < P.npts;
+                    if ((long long)base < P.npts) {
+                        const long long left = P.npts - (long long)base;
+                        sc_row = (long long)base / span;
+                        sc_next = (long long)base;
+                        sc_left = (int)((left < span ? left : span) + 31) / 32;
+                    }
+                }
+                if (sc_left > 0) {
+                    next = sc_next + (threadIdx.x & 31);
+                    sc_next += 32;
+                    sc_left--;
+                }
+            } else if (dyn) {
                 next = P.npts;
                 if (more) {  // one atomic per refill: the warp takes the next popc(idle) points of the launch
                     unsigned long long base = 0ull;

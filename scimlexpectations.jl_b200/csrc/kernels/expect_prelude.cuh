@@ -7,6 +7,7 @@
 //   #define B200E_CLIP_DTMAX  1 when the model sets dtmax < t1 - t0
 //   #define B200E_NSAVE    number of save times of a time-sampled observable (0: end-state observable)
 //   #define B200E_TABLE_PDF   1 when a factor of the density is tabulated
+//   #define B200E_DYNAMIC / B200E_REPRO   work distribution (B200E_SCHED_*): dynamic instantiations, reproducible sums
 // and the text of b200e_kparams.h.
 //
 // Dialect of the model source (valid as CUDA device code here and as C in the test oracle):
@@ -15,6 +16,9 @@
 
 #ifndef B200E_DYNAMIC
 #define B200E_DYNAMIC 0
+#endif
+#ifndef B200E_REPRO
+#define B200E_REPRO 0
 #endif
 
 #if B200E_FP32

@@ -592,3 +592,41 @@ def test_larger_state_dimension(gpu):
     k0, k1 = x[:, 0], x[:, 1]
     assert np.allclose(raw[:, 0], np.exp(-2.0 * k0), rtol=2e-3)
     assert np.allclose(raw[:, 1], k0 / (k1 - k0) * (np.exp(-2.0 * k0) - np.exp(-2.0 * k1)), rtol=5e-3, atol=1e-5)
+
+
+def test_reproducible_dynamic_schedule(gpu):
+    """schedule = DYNAMIC_REPRODUCIBLE: dynamic work distribution whose sums are bit-identical from run to run
+    AND across launch shapes (a row of sums per super-chunk of consecutive points, folded in index order),
+    with device-resident, host-chunked and in-kernel-sampled points; counters as always."""
+    for name in ("linear2", "lotka_volterra"):
+        n = 400003
+        x = sample_points(name, n, seed=51)
+        ref = None
+        for shape in (dict(block_size=64, blocks_per_sm=2), dict(block_size=128, blocks_per_sm=3), dict(block_size=32, blocks_per_sm=4)):
+            with gpu.Handle(gpu.models.builtin(name, schedule=2, **shape)) as h:
+                assert h.last_stats is not None
+                d = h.device_array(x.shape).upload(x)
+                a = h.reduce_samples(d, npts=n)
+                b = h.reduce_samples(d, npts=n)
+                assert h.last_stats()["grid"] * shape["block_size"] < n          # the dynamic kernel ran
+                g1, g2 = h.reduce_generated(6, n), h.reduce_generated(6, n)
+                d.free()
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+            assert np.array_equal(g1[0], g2[0]) and np.array_equal(g1[1], g2[1]) and g1[2] == g2[2]
+            if ref is None:
+                ref = (a, g1)
+            else:   # another launch shape: the very same bits
+                assert np.array_equal(a[0], ref[0][0]) and np.array_equal(a[1], ref[0][1]) and a[2] == ref[0][2]
+                assert np.array_equal(g1[0], ref[1][0]) and g1[2] == ref[1][2]
+        # against the plain dynamic schedule: same integers, sums to summation-order rounding
+        with gpu.Handle(gpu.models.builtin(name)) as h:
+            s, q, c = h.reduce_samples(x)
+        assert c == ref[0][2]
+        assert np.max(np.abs(s - ref[0][0]) / np.abs(s)) < 1e-12 and np.max(np.abs(q - ref[0][1]) / np.abs(q)) < 1e-12
+        # host input cut into several launches (a ragged last one that is too small for the dynamic kernel)
+        with gpu.Handle(gpu.models.builtin(name, schedule=2, chunk_points=150000, block_size=64, blocks_per_sm=2)) as h:
+            u, v = h.reduce_samples(x), h.reduce_samples(x)
+        assert np.array_equal(u[0], v[0]) and np.array_equal(u[1], v[1]) and u[2] == ref[0][2]
+        assert np.max(np.abs(u[0] - s) / np.abs(s)) < 1e-12
+    with pytest.raises(gpu.B200Error):   # only adaptive Tsit5 with an end-state observable
+        gpu.Handle(gpu.models.builtin("oscillator_noise", schedule=2))
