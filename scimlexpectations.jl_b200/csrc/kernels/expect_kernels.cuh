@@ -713,15 +713,28 @@ __device__ __forceinline__ void em_run(const b200e_kparams &P) {
     // lane takes the same number of steps, but resident warps do not advance at equal pace).  The host
     // launches the static instantiation when there is at most one point per lane.
     constexpr bool dyn = DYN;
+    // Reproducible dynamic schedule: the warp takes a super-chunk of P.super_chunks x 32 consecutive points
+    // (a whole number of pools), sums every pool over its lanes with a fixed shuffle tree, adds the pool sums
+    // in order and writes one row of sums per super-chunk (see tsit5_run).
+    constexpr bool repro = B200E_REPRO && REDUCE && DYN;
+    __shared__ double sh_wacc[repro ? NWARPS : 1][repro ? NACC : 1];
+    const int pools_per_grab = repro ? (int)(P.super_chunks / SPT) : 1;
+    if (repro) {
+        for (int k = lane; k < NACC; k += 32) sh_wacc[threadIdx.x >> 5][k] = 0.0;
+        __syncwarp();
+    }
     for (long long pool = ((long long)blockIdx.x * B200E_BLOCK + threadIdx.x) >> 5;; pool += T >> 5) {
-        long long base;
+        long long base0;
         if (dyn) {
             unsigned long long b = 0ull;
-            if (lane == 0) b = atomicAdd(P.work_counter, (unsigned long long)(32 * SPT));
-            base = (long long)__shfl_sync(B200E_FULL, b, 0);
+            if (lane == 0) b = atomicAdd(P.work_counter, (unsigned long long)(32 * SPT) * (unsigned long long)pools_per_grab);
+            base0 = (long long)__shfl_sync(B200E_FULL, b, 0);
         } else {
-            base = pool * (32 * SPT);
+            base0 = pool * (32 * SPT);
         }
+        if (base0 >= P.npts) break;
+      for (int pg = 0; pg < pools_per_grab; pg++) {
+        const long long base = base0 + (long long)pg * (32 * SPT);
         if (base >= P.npts) break;
 
         long long idx[SPT];
@@ -799,13 +812,42 @@ __device__ __forceinline__ void em_run(const b200e_kparams &P) {
         }
 #pragma unroll
         for (int q = 0; q < SPT; q++) {
+            if (repro) {  // chunk sum in a fixed order: lanes without a point contribute zeros
+                real out[NOUT];
+                observable(u[q], p[q], (real)P.t1, out);
+#pragma unroll 1
+                for (int k = 0; k < NOUT; k++) {
+                    double v = valid[q] ? (double)out[k] : 0.0;
+                    if (P.weight_by_pdf) v *= wgt[q];
+                    double v2 = v * v;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        v += __shfl_xor_sync(B200E_FULL, v, off);
+                        v2 += __shfl_xor_sync(B200E_FULL, v2, off);
+                    }
+                    if (lane == 0) {
+                        sh_wacc[threadIdx.x >> 5][k] += v;
+                        sh_wacc[threadIdx.x >> 5][NOUT + k] += v2;
+                    }
+                }
+            }
             if (!valid[q]) continue;
             int failed = 0;
 #pragma unroll
             for (int j = 0; j < N; j++) failed |= !(u[q][j] == u[q][j]);
-            emit<REDUCE>(P, idx[q], u[q], p[q], wgt[q], A);
+            if (!repro) emit<REDUCE>(P, idx[q], u[q], p[q], wgt[q], A);
             if (!REDUCE && P.steps) P.steps[idx[q]] = (int)nsteps;
             A.count((unsigned)nsteps, (unsigned)nsteps, 0u, (unsigned)failed);
+        }
+      }  // pools of this grab
+        if (repro) {  // the super-chunk is complete: its row leaves the warp
+            const long long row = base0 / ((long long)(32 * SPT) * pools_per_grab);
+            __syncwarp();
+            for (int k = lane; k < NACC; k += 32) {
+                P.chunk_rows[row * NACC + k] = sh_wacc[threadIdx.x >> 5][k];
+                sh_wacc[threadIdx.x >> 5][k] = 0.0;
+            }
+            __syncwarp();
         }
     }
     block_reduce_store<REDUCE>(P, A);
