@@ -111,10 +111,23 @@ B200E_MFN void tab_fill(b200e_tabs &T, int j) {
 
 // ---- branch-free scalar helpers -----------------------------------------------------------
 #if B200E_FP32
+// FP32 mode: the special-function unit's approximations (MUFU.RCP / LG2 / EX2 / RSQ, ~2^-22 relative) are at the
+// level of the arithmetic itself and carry no slow-path subroutine; the log clamps its argument so that 0, inf
+// and NaN error estimates saturate the controller's clamps exactly as in the FP64 path.
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+B200E_MFN float rcp_pos(float b) { return __frcp_rn(b); }
+B200E_MFN float log_pos(const b200e_tabs &, float x) {
+    const float xc = __int_as_float(min(max(__float_as_int(x), 0x00800000), 0x7f000000));  // [2^-126, 2^127]; NaN -> 2^127
+    return __logf(xc);
+}
+B200E_MFN float exp_small(const b200e_tabs &, float y) { return __expf(y); }
+B200E_MFN float sqrt_pos(float x) { return __fsqrt_rn(x); }
+#else
 B200E_MFN float rcp_pos(float b) { return 1.0f / b; }
 B200E_MFN float log_pos(const b200e_tabs &, float x) { return logf(x); }
 B200E_MFN float exp_small(const b200e_tabs &, float y) { return expf(y); }
 B200E_MFN float sqrt_pos(float x) { return sqrtf(x); }
+#endif
 #else
 // 1/b for normal b > 0: MUFU.RCP64H seed (20 bits: it reads the high word only) + one cubic step
 //   e = 1 - b r;  1/b = r / (1 - e) = r (1 + e + e^2 + O(e^3)),  e^3 <= 2^-60
