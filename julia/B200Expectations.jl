@@ -11,6 +11,8 @@
 #                                                        (reference src/expectation.jl:169-200)
 #     solve(::ExpectationProblem{<:SystemMap{..,EnsembleB200}}, ::MonteCarlo)
 #                                                        (reference src/expectation.jl:268-294)
+#     solve(::ExpectationProblem{<:SystemMap{..,EnsembleB200}}, ::Koopman, ::B200Cubature)   (optional: the whole
+#                                                        h-adaptive solve as one C call, src/expectation.jl:336-354)
 # so that `solve(exprob, Koopman(); batch=..., quadalg=CubatureJLh())` and `solve(exprob, MonteCarlo(n))`
 # keep their signatures.  Julia closures cannot run on the device: f, g, h travel as CUDA source
 # (fields of `B200Model`); `h`/`g` of the structured forms (scatter x into u0/p, end-state components)
@@ -81,14 +83,18 @@ function create_handle(exprob::ExpectationProblem, dists)
     pdf = PdfDim[pdfdim(d) for d in dists]
     src = m.rhs * "\n" * m.hmap * "\n" * m.observable
     kw = S.kwargs
+    # saveat of the ODEProblem (docs/src/tutorials/introduction.md:207-212): the observable is then an
+    # `observable_at(k, t, u, p, out)` source and nout = length(saveat) * outputs per save time
+    saves = collect(Float64, get(prob.kwargs, :saveat, Float64[]))
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve u0 p pdf src ens begin
+    GC.@preserve u0 p pdf src ens saves begin
         cm = CModel(sizeof(CModel), length(u0), length(p), length(pdf), m.nout, 0, 0, ens.fp32 ? 1 : 0,
                     Base.unsafe_convert(Cstring, src), pointer(u0), pointer(p),
                     prob.tspan[1], prob.tspan[2], get(kw, :abstol, 1e-6), get(kw, :reltol, 1e-3),
                     get(kw, :dtmax, 0.0), 0.0, get(kw, :maxiters, 100000), pointer(pdf),
                     length(ens.devices), isempty(ens.devices) ? Ptr{Int32}(C_NULL) : pointer(ens.devices),
-                    0, 0, 0, 0, ens.schedule, 0, Ptr{Float64}(C_NULL), Cstring(C_NULL))
+                    0, 0, 0, 0, ens.schedule, length(saves), isempty(saves) ? Ptr{Float64}(C_NULL) : pointer(saves),
+                    Cstring(C_NULL))
         rc = ccall((:b200e_create, LIB), Cint, (Ref{CModel}, Ref{Ptr{Cvoid}}), cm, h)
         rc == 0 || error("b200e_create: ", unsafe_string(ccall((:b200e_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
     end
@@ -111,6 +117,29 @@ function build_integrand(prob::B200Problem, ::Koopman, mid, p, batch::Integer; d
     prototype = nout == 1 ? zeros(1) : zeros(nout, 1)
     integrand_koopman_systemmap_batch!(prototype, reshape(collect(mid), size(mid)..., 1), p)   # :197-198
     return BatchIntegralFunction{true}(integrand_koopman_systemmap_batch!, prototype; max_batch = batch)
+end
+
+# ---- Koopman with the cubature heap inside the library (reference src/expectation.jl:336-354) --------
+"`quadalg = B200Cubature()`: h-adaptive Genz-Malik with the rule applied on the device (b200e_koopman_solve)."
+struct B200Cubature end
+struct CubatureOpts; reltol::Float64; abstol::Float64; maxevals::Int64; end
+struct CubatureStats
+    nevals::Int64; nrounds::Int64; nregions::Int64; max_batch::Int64
+    converged::Int32; _pad::Int32
+    kernel_ms::Float64; total_ms::Float64
+    counters::Counters
+end
+function SciMLBase.solve(exprob::B200Problem, ::Koopman, ::B200Cubature; dists = exprob.d.pdf_func.dists,
+                         ireltol = 1e-2, iabstol = 1e-2, maxiters = 1000000, kwargs...)
+    h = create_handle(exprob, dists)
+    nout = exprob.S.ensemblealg.model.nout
+    lb, ub = collect(Float64, extrema(exprob.d)[1]), collect(Float64, extrema(exprob.d)[2])
+    u = zeros(nout); resid = zeros(nout); st = Ref{CubatureStats}()
+    check(ccall((:b200e_koopman_solve, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{CubatureOpts}, Ptr{Float64}, Ptr{Float64}, Ref{CubatureStats}),
+                h, lb, ub, CubatureOpts(ireltol, iabstol, maxiters), u, resid, st), h)
+    ccall((:b200e_destroy, LIB), Cint, (Ptr{Cvoid},), h)
+    return ExpectationSolution(nout == 1 ? u[1] : u, nout == 1 ? resid[1] : resid, st[])
 end
 
 # ---- MonteCarlo (reference src/expectation.jl:268-294) ---------------------------------------------
@@ -151,5 +180,9 @@ observable_components(idx) =                                    # g(sol,p) = sol
     "B200E_FN void observable(const real* u, const real* p, real t_end, real* out) {\n" *
     join(["  out[$(k-1)] = u[$(i-1)];\n" for (k, i) in enumerate(idx)]) * "}\n"
 
-export EnsembleB200, B200Model, hmap_scatter, observable_components
+observable_at_components(idx) =                                 # g(sol,p) = sol[idx, :] with saveat / [sol(t_k)[i] ...]
+    "B200E_FN void observable_at(int k, real t, const real* u, const real* p, real* out) {\n" *
+    join(["  out[$(j-1)] = u[$(i-1)];\n" for (j, i) in enumerate(idx)]) * "}\n"
+
+export EnsembleB200, B200Model, B200Cubature, hmap_scatter, observable_components, observable_at_components
 end # module
