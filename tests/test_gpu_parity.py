@@ -632,3 +632,31 @@ def test_reproducible_dynamic_schedule(gpu):
         assert np.max(np.abs(u[0] - s) / np.abs(s)) < 1e-12
     with pytest.raises(gpu.B200Error):   # end-state observables only
         gpu.Handle(gpu.models.builtin("linear2_saveat", schedule=2))
+
+
+def test_full_size_properties_through_the_in_kernel_sampler(gpu):
+    """BASELINE configs 4 and 5 at a tenth of their full size (10^8 lorenz63 samples, 10^7 Euler-Maruyama paths;
+    the full sizes run in scripts/big_mc.py), possible only because no sample set has to exist.  Size-independent
+    properties: the stream is additive over index ranges (counters exactly, sums to rounding), the counters obey
+    their identities, and a 2^17-sample window drawn by the host twin agrees with the oracle."""
+    for name, n in (("lorenz63", 10**8), ("oscillator_noise", 10**7)):
+        with gpu.Handle(gpu.models.builtin(name)) as h:
+            s, s2, c = h.reduce_generated(99, n)
+            cut = 37 * n // 100 + 5
+            a, b = h.reduce_generated(99, cut), h.reduce_generated(99, n - cut, first_index=cut)
+            m = 1 << 17
+            first = n // 2 + 12345
+            sw, s2w, cw = h.reduce_generated(99, m, first_index=first)
+            xw = h.sample_host(99, m, first_index=first)
+        assert {k: a[2][k] + b[2][k] for k in c} == c and c["nfail"] == 0
+        assert np.max(np.abs(a[0] + b[0] - s) / np.abs(s)) < 1e-12 and np.max(np.abs(a[1] + b[1] - s2) / np.abs(s2)) < 1e-12
+        if name == "lorenz63":
+            assert c["nf"] == 3 * n + 6 * (c["naccept"] + c["nreject"])
+        else:
+            assert c["nf"] == c["naccept"] == 1024 * n
+        so, s2o, co = oracle.OracleProblem.builtin(name).reduce_samples(xw)
+        _assert_counters_match_oracle(cw, co, m)
+        assert np.max(np.abs(sw - so) / np.abs(so)) < 1e-8 and np.max(np.abs(s2w - s2o) / np.abs(s2o)) < 1e-8
+        # Monte Carlo consistency of the whole batch with its window: |mean_n - mean_m| within 6 standard errors
+        se = np.sqrt(np.maximum(s2w / m - (sw / m) ** 2, 0) / m)
+        assert np.all(np.abs(s / n - sw / m) < 6 * se)
