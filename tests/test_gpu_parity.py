@@ -630,6 +630,11 @@ def test_reproducible_dynamic_schedule(gpu):
             u, v = h.reduce_samples(x), h.reduce_samples(x)
         assert np.array_equal(u[0], v[0]) and np.array_equal(u[1], v[1]) and u[2] == ref[0][2]
         assert np.max(np.abs(u[0] - s) / np.abs(s)) < 1e-12
+        # batches smaller than the grid: the sampled kernel is dynamic at every size, the loaded one goes static
+        with gpu.Handle(gpu.models.builtin(name, schedule=2)) as h:
+            t1, t2 = h.reduce_generated(6, 1000), h.reduce_generated(6, 1000)
+            w1, w2 = h.reduce_samples(x[:1000]), h.reduce_samples(x[:1000])
+        assert np.array_equal(t1[0], t2[0]) and t1[2] == t2[2] and np.array_equal(w1[0], w2[0]) and w1[2] == w2[2]
     with pytest.raises(gpu.B200Error):   # end-state observables only
         gpu.Handle(gpu.models.builtin("linear2_saveat", schedule=2))
 
