@@ -665,3 +665,28 @@ def test_full_size_properties_through_the_in_kernel_sampler(gpu):
         # Monte Carlo consistency of the whole batch with its window: |mean_n - mean_m| within 6 standard errors
         se = np.sqrt(np.maximum(s2w / m - (sw / m) ** 2, 0) / m)
         assert np.all(np.abs(s / n - sw / m) < 6 * se)
+
+
+def test_untruncated_normal_factor(gpu):
+    """A plain Normal factor (infinite support): pdf weight against the oracle, sampler against the host twin and
+    against scipy's distribution; the far tails go through the third branch of AS241."""
+    import scipy.stats as st
+    pdf = [(gpu._capi.PDF_NORMAL, -np.inf, np.inf, 5.0, 1.5), (gpu._capi.PDF_TRUNCNORMAL, 0.0, 6.0, 3.0, 1.0)]
+    spec = gpu.models.builtin("linear2", pdf=pdf)
+    n = 200003
+    xh = gpu.sample_host(spec, 11, n)
+    orc = oracle.OracleProblem.builtin("linear2")
+    orc.set_pdf(pdf)
+    ref, cref = orc.eval_nodes(xh, weight_by_pdf=True)
+    with gpu.Handle(spec) as h:
+        xd = h.sample_device(11, n)
+        dx = h.eval_nodes(xh, weight_by_pdf=True)
+        c = h.last_counters()
+        sg, _, cg = h.reduce_generated(11, n)
+        sx, _, cx = h.reduce_samples(xh)
+    assert np.array_equal(xd.view(np.uint64), xh.view(np.uint64))
+    assert st.kstest(xh[:, 0], st.norm(5.0, 1.5).cdf).pvalue > 1e-4 and np.abs(xh[:, 0]).max() < 5.0 + 1.5 * 6
+    assert c == cref and cg == cx
+    med, mx = _node_err(dx, ref)
+    assert med <= 1e-10 and mx <= 2e-6
+    assert np.max(np.abs(sg - sx) / np.abs(sx)) < 1e-12
