@@ -694,7 +694,8 @@ constexpr int NK = B200E_NKKL;
 // to all 32 lanes: 64 B x 32 lanes per step saturate the LSU write-back path (ncu: l1tex lsu_writeback_active
 // 90 %, long-scoreboard stalls 55 %, FP64 pipe 52 %) long before the FP64 pipe.  A lane that integrates two
 // samples side by side uses each loaded row twice: half the load traffic per sample, and the step becomes
-// FP64-bound again (measured 3.96 -> 2.9 ms on C5).
+// FP64-bound again (measured 3.96 -> 2.57 ms on C5 with two samples per thread at two blocks of 256, 2.36 ms
+// with three at three blocks of 128: the host's default).
 #ifndef B200E_EM_SPT
 #define B200E_EM_SPT 2
 #endif
