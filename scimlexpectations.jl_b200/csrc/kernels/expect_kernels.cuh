@@ -8,15 +8,18 @@
 //   output_func src/expectation.jl:180, :227 (g * pdf)  and :282, :316 (g)
 //   reduction   src/expectation.jl:194 (dx .= ...)  and :293, :324 (mean(sol.u) -> sums here)
 //
-// Execution model: ONE trajectory per thread, state and step control in registers.  Every lane
-// owns the static sample sequence i = tid, tid+T, tid+2T, ... (T = grid*block), so the mapping
-// sample -> lane -> accumulator is fixed by the launch shape alone: sums are reproducible and
-// the step counters are exact integers.  Adaptive step counts differ between lanes; instead of a
-// nested per-trajectory loop (warp runs as long as its slowest lane) the loop body is "one RK
-// step of my current trajectory", and idle lanes are re-loaded together once at least
-// `refill_threshold` lanes of the warp are idle -- the reload (h, pdf, initial-dt heuristic, two
-// extra RHS evaluations) costs about one step and would otherwise run under a divergent mask for
-// every single finishing lane.
+// Execution model: ONE trajectory per thread (two or three side by side in the Euler-Maruyama kernel), state
+// and step control in registers; every block is resident (grid = SMs x resident blocks).  Adaptive step
+// counts differ between lanes; instead of a nested per-trajectory loop (warp runs as long as its slowest
+// lane) the loop body is "one RK step of my current trajectory", and idle lanes are re-loaded together once
+// at least `refill_threshold` lanes of the warp are idle -- the reload (h, pdf, initial-dt heuristic, two
+// extra RHS evaluations) costs about one step and would otherwise run under a divergent mask for every
+// single finishing lane.  Which point a lane gets next is either fixed by the launch shape (static: lane l
+// owns points l, l+T, l+2T, ...; sums reproducible) or decided at run time off a device counter (dynamic:
+// no warp waits for work another one still owns; optionally with one row of sums per super-chunk of
+// consecutive points so that the sums stay reproducible).  A point's own result -- its outputs, its step
+// counters -- never depends on that choice.  Five instantiations per model: b200e_nodes, b200e_reduce
+// (static), b200e_nodes_dyn, b200e_reduce_dyn (dynamic), b200e_reduce_gen (points drawn in the kernel).
 
 #define B200E_FULL 0xffffffffu
 
