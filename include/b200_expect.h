@@ -180,6 +180,14 @@ int b200e_eval_nodes(b200e_handle *h, const double *x, int64_t npts, int32_t lay
 int b200e_reduce_samples(b200e_handle *h, const double *x, int64_t n, int32_t layout,
                          int32_t weight_by_pdf, double *sum, double *sumsq, b200e_counters *c);
 
+/* The same reduction split in two for device-resident points on a single-device handle: _begin enqueues the
+ * kernel (and the copy of its 2*nout + 4 results) and returns, _end waits and hands the results over.  A caller
+ * with an exchange step of its own -- one process per GPU, the all-reduce of the previous batch -- puts that step
+ * between the two and overlaps it with the kernel.  One reduction may be pending per handle; x must stay valid
+ * and unchanged until _end returns. */
+int b200e_reduce_samples_begin(b200e_handle *h, const double *x, int64_t n, int32_t layout, int32_t weight_by_pdf);
+int b200e_reduce_samples_end(b200e_handle *h, double *sum, double *sumsq, b200e_counters *c);
+
 /* counters of the last b200e_eval_nodes call */
 int b200e_last_counters(const b200e_handle *h, b200e_counters *c);
 int b200e_last_stats(const b200e_handle *h, b200e_call_stats *s);

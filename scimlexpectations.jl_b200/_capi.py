@@ -37,6 +37,7 @@ EXPORTS = [
     "b200e_device_alloc", "b200e_device_free", "b200e_memcpy_h2d", "b200e_memcpy_d2h",
     "b200e_measure_fma_peak", "b200e_device_count", "b200e_eval_regions", "b200e_koopman_solve",
     "b200e_reduce_generated", "b200e_sample_host", "b200e_sample_device",
+    "b200e_reduce_samples_begin", "b200e_reduce_samples_end",
 ]
 
 
@@ -142,6 +143,8 @@ def load_library():
     L.b200e_eval_regions.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200e_koopman_solve.argtypes = [H, C.c_void_p, C.c_void_p, C.POINTER(CubatureOpts), C.c_void_p, C.c_void_p,
                                       C.POINTER(CubatureStats)]
+    L.b200e_reduce_samples_begin.argtypes = [H, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
+    L.b200e_reduce_samples_end.argtypes = [H, C.c_void_p, C.c_void_p, C.POINTER(Counters)]
     L.b200e_reduce_generated.argtypes = [H, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(Counters)]
     L.b200e_sample_host.argtypes = [C.POINTER(Model), C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_void_p]
     L.b200e_sample_device.argtypes = [H, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_void_p]
@@ -491,6 +494,21 @@ class Handle:
         self._check(self.L.b200e_eval_regions(self._h, c.ctypes.data, w.ctypes.data, n, val.ctypes.data,
                                               err.ctypes.data, split.ctypes.data))
         return val, err, split
+
+    def reduce_samples_begin(self, x, *, npts, layout=LAYOUT_POINT_MAJOR, weight_by_pdf=False):
+        """Enqueue the reduction of device-resident points and return at once (``reduce_samples_end`` waits)."""
+        xp, xk = _as_pointer(x, None)
+        self._check(self.L.b200e_reduce_samples_begin(self._h, xp, int(npts), int(layout), int(bool(weight_by_pdf))))
+        self._pending_keep = xk
+
+    def reduce_samples_end(self):
+        """Wait for the pending reduction: ``(sum, sumsq, counters)``."""
+        s = np.zeros(self.spec.nout)
+        s2 = np.zeros(self.spec.nout)
+        c = Counters()
+        self._check(self.L.b200e_reduce_samples_end(self._h, s.ctypes.data, s2.ctypes.data, C.byref(c)))
+        self._pending_keep = None
+        return s, s2, c.as_dict()
 
     def reduce_generated(self, seed: int, n: int, *, first_index: int = 0):
         """``solve(exprob, MonteCarlo(n))`` with ``rand(d)`` drawn inside the kernel (reference

@@ -690,3 +690,27 @@ def test_untruncated_normal_factor(gpu):
     med, mx = _node_err(dx, ref)
     assert med <= 1e-10 and mx <= 2e-6
     assert np.max(np.abs(sg - sx) / np.abs(sx)) < 1e-12
+
+
+def test_split_reduce_call(gpu):
+    """b200e_reduce_samples_begin / _end: the device-resident reduction in two halves (a caller's own exchange
+    step goes in between).  Same results as the blocking call; one reduction pending per handle."""
+    name = "lorenz63"
+    n = 200001
+    x = sample_points(name, n, seed=61)
+    with gpu.Handle(gpu.models.builtin(name, schedule=2)) as h:
+        d = h.device_array(x.shape).upload(x)
+        ref = h.reduce_samples(d, npts=n)
+        h.reduce_samples_begin(d, npts=n)
+        with pytest.raises(gpu.B200Error):
+            h.reduce_samples_begin(d, npts=n)             # one pending reduction per handle
+        with pytest.raises(gpu.B200Error):
+            h.reduce_samples(d, npts=n)
+        got = h.reduce_samples_end()
+        with pytest.raises(gpu.B200Error):
+            h.reduce_samples_end()                        # nothing pending any more
+        with pytest.raises(gpu.B200Error):
+            h.reduce_samples_begin(x, npts=n)             # host memory: the split form is for resident points
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+        assert h.last_stats()["kernel_ms"] > 0
+        d.free()
