@@ -368,6 +368,16 @@ def run_b200(args):
     e_steps = max(3, args.steps // 4)
     Tg, g_kernel_ms, _, _, (sg, s2g, cg, stg) = timed(step_generated, args.steps, 3)
 
+    # per-rank device times and clocks (outside the timed regions): the job moves at the pace of its slowest GPU
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([float(np.mean(kernel_ms)), float(np.mean(total_ms)), float(clocks.get("sm_mhz") or 0.0)],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"kernel_ms": [round(float(t[0]), 4) for t in allr], "device_ms_per_step": [round(float(t[1]), 4) for t in allr],
+                    "sm_mhz": [float(t[2]) for t in allr]}
+
     value = world * n * args.steps / T
     e2e_value = world * n * e_steps / Te
     k_ms = float(np.mean(kernel_ms))
@@ -416,6 +426,8 @@ def run_b200(args):
             "counters": c, "expectation": mean.tolist(),
             "device_ms_per_step": float(np.mean(total_ms)),
         }
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if world == 1 and not args.no_solves:
             line["expectation_solves"] = time_koopman_solves("b200")
         if world == 1 and not args.no_cpu:
