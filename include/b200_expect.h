@@ -14,6 +14,12 @@
  *                            (the f!(dx, x, p) Integrals.jl calls once per cubature refinement round)
  *   b200e_reduce_samples  <- solve(exprob, MonteCarlo(n)): the EnsembleProblem solve + mean(sol.u)
  *                                                                             src/expectation.jl:277-293, :304-324
+ *   b200e_reduce_samples_begin / _end
+ *                         <- the same reduction in two halves (device-resident points): a caller's own exchange
+ *                            step overlaps the next kernel
+ *   b200e_reduce_generated <- the same solve with rand(d) of prob_func (src/expectation.jl:278,
+ *                            src/distribution_utils.jl:43) drawn inside the kernel from a counter-based stream;
+ *                            b200e_sample_host / b200e_sample_device reproduce that stream bit for bit
  *   b200e_eval_regions    <- the Genz-Malik rule Cubature's hcubature_v applies to the dx it gets back from
  *                            the integrand callback (third-party C library behind src/expectation.jl:361-362;
  *                            SURVEY.md 8f rank 1): regions in, (value, error, split dimension) per region out
@@ -22,7 +28,8 @@
  *
  * Conventions: every function returns 0 on success and a negative B200E_ERR_* code on failure;
  * b200e_last_error(h) returns a message owned by the library.  All host buffers are caller-owned;
- * the library copies in/out inside the call and keeps no caller pointer after it returns.  Calls on
+ * the library copies in/out inside the call and keeps no caller pointer after it returns (the one exception is
+ * spelled out at b200e_reduce_samples_begin).  Calls on
  * one handle are serialised by the caller; distinct handles may be used from distinct threads.
  * x / dx / sum pointers may be HOST pointers (pageable or pinned) or DEVICE pointers on the
  * handle's device (detected with cudaPointerGetAttributes); device pointers skip the copies.
