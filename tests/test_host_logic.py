@@ -175,3 +175,19 @@ def test_world_size_2_exchange_step_over_gloo(sme):
     s, s2, c = oracle.OracleProblem.builtin("lorenz63").reduce_samples(x)
     assert Cn == c                                   # integer bookkeeping is exact across ranks
     assert np.allclose(S, s, rtol=1e-13) and np.allclose(S2, s2, rtol=1e-13)
+
+
+def test_bench_reference_arm_runs_on_the_cpu_box():
+    """`bench.py --impl reference` (the driver's reference arm: the CPU restatement of the path on all host
+    cores) needs no GPU and prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3",
+                          "--no-solves"], check=True, capture_output=True, text=True, timeout=600).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "ODE-solve integrand evals/sec" and line["value"] > 1e4
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["config"]["workload"] == "linear2_mc1e7" and line["higher_is_better"] is True
