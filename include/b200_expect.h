@@ -64,7 +64,12 @@ enum {
     B200E_ERR_NCCL = -6
 };
 
-enum { B200E_SOLVER_TSIT5 = 0, B200E_SOLVER_EM = 1 };
+/* TSIT5: adaptive Tsit5 (the ODE path, src/expectation.jl:191 / :290).  EM: fixed-step Euler-Maruyama
+ * driven by the KKL noise path (src/expectation.jl:215-225 / :304-314 with dt = dt_fixed).  LAMBA_EM: the
+ * same path with StochasticDiffEq's adaptive `LambaEM`, the solver the reference's own process-noise test
+ * uses (test/processnoise.jl:15: ProcessNoiseSystemMap(prob, 8, LambaEM(), abstol, reltol)); tolerances
+ * from abstol / reltol, dt_fixed unused. */
+enum { B200E_SOLVER_TSIT5 = 0, B200E_SOLVER_EM = 1, B200E_SOLVER_LAMBA_EM = 2 };
 enum { B200E_FP64 = 0, B200E_FP32 = 1 };
 /* layout of x (and dx): 0 = point-major x[i*nx+j] (what Julia's dim x npts column-major array is),
  *                        1 = SoA x[j*npts+i] */
@@ -116,13 +121,13 @@ typedef struct {
     uint32_t struct_size; /* sizeof(b200e_model), for ABI evolution */
     int32_t nstate, nparam, nx, nout;
     int32_t solver;  /* B200E_SOLVER_* */
-    int32_t n_kkl;   /* EM: number of KKL terms (length of Z); 0 for Tsit5 */
+    int32_t n_kkl;   /* EM / LAMBA_EM: number of KKL terms (length of Z); 0 for Tsit5 */
     int32_t fp_mode; /* B200E_FP64 / B200E_FP32 (state arithmetic; accumulation is always f64) */
     const char *source;
     const double *u0; /* nominal initial condition, nstate entries (prob.u0) */
     const double *p;  /* nominal parameters, nparam entries (prob.p) */
     double t0, t1;    /* prob.tspan */
-    double abstol, reltol; /* Tsit5 tolerances (OrdinaryDiffEq defaults 1e-6 / 1e-3) */
+    double abstol, reltol; /* Tsit5 / LambaEM tolerances (OrdinaryDiffEq defaults 1e-6 / 1e-3) */
     double dtmax;          /* <= 0 -> t1 - t0 */
     double dt_fixed;       /* EM step */
     int64_t maxiters;      /* <= 0 -> 100000 */

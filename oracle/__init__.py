@@ -23,7 +23,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libexpect_oracle.so")
 
 ORC_MAX_STATE, ORC_MAX_PARAM, ORC_MAX_X, ORC_MAX_OUT, ORC_MAX_KKL, ORC_MAX_SAVE = 16, 32, 32, 64, 32, 64
 PDF_NONE, PDF_UNIFORM, PDF_NORMAL, PDF_TRUNCNORMAL = 0, 1, 2, 3
-SOLVER_TSIT5, SOLVER_EM = 0, 1
+SOLVER_TSIT5, SOLVER_EM, SOLVER_LAMBA_EM = 0, 1, 2
 
 RHS_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double)
 MAP_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -121,7 +121,7 @@ class OracleProblem:
         The source defines ``rhs``, ``hmap``, ``observable`` (and ``diffusion`` for EM) with
         ``B200E_FN`` linkage and ``real`` scalars; here ``real`` is double."""
         save_times = [float(t) for t in save_times]
-        so = _compile_model(src, has_diffusion=(solver == SOLVER_EM), has_obs_at=bool(save_times))
+        so = _compile_model(src, has_diffusion=(solver != SOLVER_TSIT5), has_obs_at=bool(save_times))
         m = C.CDLL(so)
         st = Problem()
         st.nstate, st.nparam, st.nx, st.nout = nstate, nparam, nx, nout
@@ -137,7 +137,7 @@ class OracleProblem:
             keep_extra.append(ta)
         else:
             st.obs = C.cast(m.orc_model_obs, C.c_void_p)
-        if solver == SOLVER_EM:
+        if solver != SOLVER_TSIT5:
             st.diffusion = C.cast(m.orc_model_diffusion, C.c_void_p)
         u0a = (C.c_double * max(1, nstate))(*[float(v) for v in u0])
         pa = (C.c_double * max(1, nparam))(*[float(v) for v in p])
@@ -171,8 +171,8 @@ class OracleProblem:
                 self.st.t0, self.st.t1 = float(v[0]), float(v[1])
             elif k in ("abstol", "reltol", "dtmax", "dt_fixed", "t0", "t1"):
                 setattr(self.st, k, float(v))
-            elif k == "maxiters":
-                self.st.maxiters = int(v)
+            elif k in ("maxiters", "solver"):
+                setattr(self.st, k, int(v))
             else:
                 raise TypeError(f"unknown oracle option {k}")
         return self

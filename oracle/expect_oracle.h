@@ -60,20 +60,20 @@ typedef struct {
     int64_t ntable;
 } orc_pdf_dim;
 
-enum { ORC_SOLVER_TSIT5 = 0, ORC_SOLVER_EM = 1 };
+enum { ORC_SOLVER_TSIT5 = 0, ORC_SOLVER_EM = 1, ORC_SOLVER_LAMBA_EM = 2 };
 
 typedef struct {
     int32_t nstate, nparam, nx, nout;
     int32_t solver;   /* ORC_SOLVER_* */
-    int32_t n_kkl;    /* EM only: number of KKL terms (= length of Z) */
+    int32_t n_kkl;    /* EM / LambaEM: number of KKL terms (= length of Z) */
     orc_rhs_fn rhs;
-    orc_rhs_fn diffusion; /* EM only: g(du,u,p,t), scalar noise multiplies every component */
+    orc_rhs_fn diffusion; /* EM / LambaEM: g(du,u,p,t), scalar noise multiplies every component */
     orc_map_fn hmap;
     orc_obs_fn obs;
     const double *u0_nom;
     const double *p_nom;
     double t0, t1;
-    double abstol, reltol; /* Tsit5; OrdinaryDiffEq defaults 1e-6 / 1e-3 */
+    double abstol, reltol; /* Tsit5 (OrdinaryDiffEq defaults 1e-6 / 1e-3) and LambaEM */
     double dtmax;          /* <=0 -> t1-t0 */
     double dt_fixed;       /* EM step */
     int64_t maxiters;      /* <=0 -> 100000 */

@@ -7,7 +7,7 @@ from . import _capi, api, cubature, models  # noqa: F401
 from ._capi import (B200Error, DeviceArray, Handle, ModelSpec, PinnedArray, compile_check, device_count, sample_host,  # noqa: F401
                     load_library, measure_fma_peak)
 from .api import (EM, B200Cubature, BatchIntegralFunction, CubatureJLh, EnsembleB200, ExpectationProblem,  # noqa: F401
-                  ExpectationSolution, GenericDistribution, Koopman, MonteCarlo, Normal, ODEProblem,
+                  ExpectationSolution, GenericDistribution, Koopman, LambaEM, MonteCarlo, Normal, ODEProblem,
                   ProcessNoiseSystemMap, SDEProblem, SystemMap, Truncated, Tsit5, Uniform, UnivariateKDE, build_integrand,
                   centralmoment,
                   extrema, maximum, minimum, pdf, rand, solve, truncated)

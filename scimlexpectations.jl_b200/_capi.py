@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libb200expect.so")
 ABI_VERSION = 4
 MAX_STATE, MAX_PARAM, MAX_X, MAX_OUT, MAX_KKL, MAX_SAVE = 16, 32, 32, 64, 32, 64
 OK, ERR_INVALID, ERR_COMPILE, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
-SOLVER_TSIT5, SOLVER_EM = 0, 1
+SOLVER_TSIT5, SOLVER_EM, SOLVER_LAMBA_EM = 0, 1, 2
 FP64, FP32 = 0, 1
 LAYOUT_POINT_MAJOR, LAYOUT_SOA = 0, 1
 PDF_NONE, PDF_UNIFORM, PDF_NORMAL, PDF_TRUNCNORMAL, PDF_TABLE = 0, 1, 2, 3, 4

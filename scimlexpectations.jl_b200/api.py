@@ -224,6 +224,13 @@ class EM:
     dt: float = 0.0
 
 
+@dataclass(frozen=True)
+class LambaEM:
+    """Adaptive Euler-Maruyama with StochasticDiffEq's defaults (test/processnoise.jl:15); tolerances come
+    from the ``abstol`` / ``reltol`` kwargs of ``ProcessNoiseSystemMap`` (SciML defaults 1e-2 / 1e-2 for SDEs)."""
+    pass
+
+
 @dataclass
 class EnsembleB200:
     """The ``ensemblealg`` that routes the ensemble solve to libb200expect (``<: EnsembleAlgorithm``
@@ -250,8 +257,8 @@ class ProcessNoiseSystemMap:
     def __init__(self, prob: SDEProblem, n: int, *args, **kwargs):
         self.prob = prob
         self.n = int(n)
-        self.args = args      # (EM(dt),) -- forwarded solve arguments
-        self.kwargs = kwargs  # dt=..., ensemblealg=EnsembleB200(...)
+        self.args = args      # (EM(dt),) or (LambaEM(),) -- forwarded solve arguments
+        self.kwargs = kwargs  # dt=... / abstol=..., reltol=..., ensemblealg=EnsembleB200(...)
 
 
 class ExpectationProblem:
@@ -291,15 +298,19 @@ class ExpectationProblem:
         prob = S.prob
         if isinstance(S, ProcessNoiseSystemMap):
             ens = S.kwargs.get("ensemblealg", EnsembleB200())
-            alg = next((a for a in S.args if isinstance(a, EM)), None)
+            alg = next((a for a in S.args if isinstance(a, (EM, LambaEM))), None)
             if alg is None:
-                raise NotImplementedError("the B200 process-noise path implements fixed-step EM(); pass EM(dt) in args")
-            dt = float(S.kwargs.get("dt", alg.dt))
-            if not dt > 0:
+                raise NotImplementedError("the B200 process-noise path implements EM(dt) and LambaEM(); pass one in args")
+            adaptive = isinstance(alg, LambaEM)
+            dt = 0.0 if adaptive else float(S.kwargs.get("dt", alg.dt))
+            if not adaptive and not dt > 0:
                 raise ValueError("EM needs dt > 0")
             src = prob.f + "\n" + prob.g + "\n" + self.h + "\n" + self.g
             return ModelSpec(source=src, nstate=len(prob.u0), nparam=len(prob.p), nx=len(self.d), nout=self.nout,
-                             u0=list(prob.u0), p=list(prob.p), tspan=tuple(prob.tspan), solver=_capi.SOLVER_EM,
+                             u0=list(prob.u0), p=list(prob.p), tspan=tuple(prob.tspan),
+                             solver=_capi.SOLVER_LAMBA_EM if adaptive else _capi.SOLVER_EM,
+                             abstol=float(S.kwargs.get("abstol", 1e-2)), reltol=float(S.kwargs.get("reltol", 1e-2)),
+                             dtmax=float(S.kwargs.get("dtmax", 0.0)), maxiters=int(S.kwargs.get("maxiters", 100000)),
                              n_kkl=S.n, dt_fixed=dt, pdf=self.d.table(), fp_mode=FP32 if ens.fp32 else FP64,
                              devices=ens.devices, block_size=ens.block_size, blocks_per_sm=ens.blocks_per_sm,
                              refill_threshold=ens.refill_threshold, chunk_points=ens.chunk_points,

@@ -251,15 +251,22 @@ __device__ __forceinline__ void block_reduce_store(const b200e_kparams &P, Accum
     }
 }
 
-#if B200E_SOLVER == 0
+#if B200E_SOLVER != 1
 // ------------------------------------------------------------------------------------------
-// Adaptive Tsit5 (Tsitouras 2011) with OrdinaryDiffEq's defaults: Hairer-Wanner initial step,
-// PI controller beta1=7/50 beta2=2/25 gamma=9/10 qmin=1/5 qmax=10 qoldinit=1e-4, RMS error norm.
+// The adaptive solvers share one driver (adaptive_run: refill phase + step phase, work distribution,
+// accumulators) and differ in how a lane starts a trajectory and takes one attempted step:
+//   B200E_SOLVER 0  Tsit5 (Tsitouras 2011) with OrdinaryDiffEq's defaults: Hairer-Wanner initial step,
+//                   PI controller beta1=7/50 beta2=2/25 gamma=9/10 qmin=1/5 qmax=10 qoldinit=1e-4, RMS norm;
+//   B200E_SOLVER 2  LambaEM (adaptive Euler-Maruyama, the solver of reference test/processnoise.jl:15)
+//                   driven by the KKL path, StochasticDiffEq's defaults (see lamba_step).
 // Constants (KC / K_), the table-driven log / exp and the reciprocal live in expect_math.cuh.
 // ------------------------------------------------------------------------------------------
 __shared__ b200e_tabs sh_tab;
 
 enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
+
+#if B200E_SOLVER == 0
+constexpr unsigned NF_PER_ATTEMPT = 6u;  // RHS evaluations per attempted step
 
 // prob_func + integrator init for one lane: x -> (u0, p) via h, pdf weight, initial dt, FSAL k1
 template <bool GEN>
@@ -484,6 +491,180 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     }
 }
 
+#else  // B200E_SOLVER == 2
+// ------------------------------------------------------------------------------------------
+// LambaEM: Euler-Maruyama with the Lamba / Rackauckas error estimate and the SDE PI controller
+// (StochasticDiffEq; not vendored with the reference, restated from package knowledge -- the oracle's
+// lamba_solve carries the same statement and the "parity unpinned" note):
+//   K = u + dt f(u,t);  L = g(K, t+dt);  u' = K + L dW,  dW = W(t+dt) - W(t)   (NoiseFunction, split step)
+//   Ed = dt (f(K,t+dt) - f(u,t)) / 2;   En = (g(u + L sqrt(dt), t) - L) / sqrt(dt) * dW^2 / 2
+//   EEst = RMS_i( (|Ed_i| + |En_i|) / (abstol + max(|u_i|,|u'_i|) reltol) )
+//   beta1 = 7/10, beta2 = 2/5, gamma = 9/10, qmin = 1/5, qmax = 1.125, qoldinit = 1e-4.
+// W(t) = sum_k Z_k sqrt(2) sin((k-1/2) pi t) / ((k-1/2) pi) is needed at arbitrary t here (no table as in
+// the fixed-step kernel): ONE sincospi and the three-term recurrence
+//   s_{k+1} = 2 cos(pi t) s_k - s_{k-1},  s_k = sin((k-1/2) pi t),  s_0 = -s_1
+// give all NK modes in 2 DFMAs each; the reference evaluates NK sines per query (src/expectation.jl:217-220).
+// ------------------------------------------------------------------------------------------
+constexpr unsigned NF_PER_ATTEMPT = 2u;  // drift evaluations per attempted step
+constexpr int NK = B200E_NKKL;
+
+struct Lane {
+    real u[N], zc[NK], p[B200E_DIM(NP)];  // zc_k = Z_k sqrt(2) / ((k-1/2) pi)
+    real t, dt, le2old, wcur;
+    int state;
+    int failed;
+    unsigned nf0, nacc, nrej;
+    int ksave;
+};
+struct SaveCtx {
+    const b200e_kparams &P;
+    long long point;
+    double wgt;
+    Accum &A;
+};
+
+__device__ __forceinline__ real kkl_w(const real *zc, const real t) {
+    real s, c;
+#if B200E_FP32
+    sincospif(R_(0.5) * t, &s, &c);
+#else
+    sincospi(R_(0.5) * t, &s, &c);
+#endif
+    const real c2 = fma(R_(-4.0) * s, s, R_(2.0));  // 2 cos(pi t) = 2 - 4 sin^2(pi t / 2)
+    real sp = -s, sk = s, w = R_(0.0);
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        w = fma(zc[k], sk, w);
+        const real sn = fma(c2, sk, -sp);
+        sp = sk;
+        sk = sn;
+    }
+    return w;
+}
+
+// prob_func (src/expectation.jl:215-225: Z, p = h(x, u0, p); u0 stays nominal) + sde_determine_initdt
+template <bool GEN>
+__device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long long i, Lane &L, double &wgt) {
+    double xs[NX];
+    load_point<GEN>(P, i, xs);
+    wgt = P.weight_by_pdf ? pdf_weight(P, xs) : 1.0;
+    real xr[NX], u0n[N], pn[B200E_DIM(NP)], z[NK];
+#pragma unroll
+    for (int j = 0; j < NX; j++) xr[j] = (real)xs[j];
+#pragma unroll
+    for (int j = 0; j < N; j++) { u0n[j] = (real)P.u0_nom[j]; L.u[j] = u0n[j]; }
+#pragma unroll
+    for (int j = 0; j < NP; j++) { pn[j] = (real)P.p_nom[j]; L.p[j] = pn[j]; }
+#pragma unroll
+    for (int k = 0; k < NK; k++) z[k] = R_(0.0);
+    hmap(xr, u0n, pn, z, L.p);
+#pragma unroll
+    for (int k = 0; k < NK; k++) L.zc[k] = z[k] * R_(1.4142135623730951 / ((k + 0.5) * 3.14159265358979323846));
+    const real *u = L.u, *p = L.p;
+    const real t = (real)P.t0;
+    const real abstol = (real)P.abstol, reltol = (real)P.reltol, dtmax = (real)P.dtmax;
+    // sde_determine_initdt on squared norms; max(|f + 3g|, |f - 3g|) = |f| + 3|g| exactly
+    real f0[N], g0[N], isk[N];
+    rhs(f0, u, p, t);
+    diffusion(g0, u, p, t);
+    real s0 = R_(0.0), s1 = R_(0.0);
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        isk[j] = rcp_pos(fma(fabs(u[j]), reltol, abstol));
+        g0[j] = R_(3.0) * fabs(g0[j]);
+        const real a = u[j] * isk[j], b = (fabs(f0[j]) + g0[j]) * isk[j];
+        s0 = fma(a, a, s0);
+        s1 = fma(b, b, s1);
+    }
+    const real tiny2 = R_(1e-10) * R_(N);
+    real dt0 = (s0 < tiny2 || s1 < tiny2) ? R_(1e-6) : R_(0.01) * sqrt_pos(s0 * rcp_pos(s1));
+    dt0 = fmin(dt0, dtmax);
+    real u1[N], f1[N], g1[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) u1[j] = fma(dt0, f0[j], u[j]);
+    rhs(f1, u1, p, t + dt0);
+    diffusion(g1, u1, p, t + dt0);
+    real s2 = R_(0.0);
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        // max(|g0 - g1|, |g0 + g1|) = |g0| + |g1|;  max(|df + dg|, |df - dg|) = |df| + dg
+        const real d = (fabs(f1[j] - f0[j]) + (g0[j] + R_(3.0) * fabs(g1[j]))) * isk[j];
+        s2 = fma(d, d, s2);
+    }
+    const real idt0 = rcp_pos(dt0);
+    const real m2 = fmax(s1, s2 * idt0 * idt0) * R_(lit::inv_n);  // max(d1, d2)^2
+    // order 1/2: dt1 = 10^(-(2 + log10 dmax) / (order + 1/2)) = 0.01 / dmax
+    const real dt1 = (m2 <= R_(1e-30)) ? fmax(R_(1e-6), dt0 * R_(1e-3)) : R_(0.01) * rcp_pos(sqrt_pos(m2));
+    L.t = t;
+    L.dt = fmin(fmin(R_(100.0) * dt0, dt1), dtmax);
+    L.wcur = kkl_w(L.zc, t);
+    L.le2old = K_(le2_qoldinit);
+    L.nf0 += 2u;
+}
+
+template <bool REDUCE>
+__device__ __forceinline__ void lamba_step(Lane &L, const real t1, const real dtmax, const real abstol,
+                                           const real reltol, const real snap_tol, const int maxiters,
+                                           const real one_plus_eps) {
+    real *u = L.u, *p = L.p;
+    const real t = L.t;
+    const real dt = pmin(L.dt, t1 - t);  // modify_dt_for_tstops!
+    const real tnext = t + dt;
+    if (L.failed || (int)(L.nacc + L.nrej) >= maxiters || same_value(tnext, t)) {
+        L.failed = 1;
+        L.state = LANE_DONE;
+        return;
+    }
+    real f0[N], K[N], Lg[N], un[N], f1[N], v[N], g1[N];
+    rhs(f0, u, p, t);
+#pragma unroll
+    for (int i = 0; i < N; i++) K[i] = fma(dt, f0[i], u[i]);
+    diffusion(Lg, K, p, tnext);
+    const real wn = kkl_w(L.zc, tnext), dW = wn - L.wcur;
+#pragma unroll
+    for (int i = 0; i < N; i++) un[i] = fma(Lg[i], dW, K[i]);
+    rhs(f1, K, p, tnext);
+    const real sq = sqrt_pos(dt);
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = fma(Lg[i], sq, u[i]);
+    diffusion(g1, v, p, t);
+    const real hdt = R_(0.5) * dt, hw = R_(0.5) * dW * dW * rcp_pos(sq);
+    real ss = R_(0.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const real Ed = hdt * (f1[i] - f0[i]), En = (g1[i] - Lg[i]) * hw;
+        const real sc = fma(pmax(abs_bits(u[i]), abs_bits(un[i])), reltol, abstol);
+        const real r = (abs_bits(Ed) + abs_bits(En)) * rcp_pos(sc);
+        ss = fma(r, r, ss);
+    }
+    const real e2 = ss * R_(lit::inv_n);                // EEst^2
+    const bool accept = le_nonneg(e2, one_plus_eps);    // false for a NaN
+    // PI controller in log space on e2 (see tsit5_step): EEst^b1 = e2^(b1/2)
+    const real le2 = log_pos(sh_tab, e2);
+    const real hist = accept ? L.le2old : R_(0.0);
+    real qinv = exp_small(sh_tab, fma(R_(0.2), hist, fma(R_(-0.35), le2, K_(ln_gamma))));  // gamma qold^b2 / EEst^b1
+    qinv = pmin(R_(1.125), pmax(K_(qmin), qinv));
+    L.dt = dt * qinv;
+#if B200E_CLIP_DTMAX
+    L.dt = pmin(dtmax, L.dt);
+#endif
+    if (accept) {
+        L.le2old = max_with_negative(le2, R_(lit::le2_qoldinit));
+        const real left = t1 - tnext;
+        const bool snap = lt_nonneg(abs_bits(left), snap_tol);  // fixed_t_for_floatingpoint_error!
+        L.t = snap ? t1 : tnext;
+#pragma unroll
+        for (int i = 0; i < N; i++) u[i] = un[i];
+        L.wcur = wn;
+        L.nacc++;
+        if (snap || is_negative(left)) L.state = LANE_DONE;
+    } else {
+        L.failed = (e2 == e2) ? 0 : 2;
+        L.nrej++;
+    }
+}
+#endif  // solver-specific start / step
+
 template <bool REDUCE, bool DYN, bool GEN>
 __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     // Work distribution.  Static: lane l owns points l, l+T, l+2T, ... (T = grid * block).  Dynamic:
@@ -499,6 +680,9 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
 
     Lane L;
     L.t = R_(0.0); L.dt = R_(0.0); L.le2old = R_(0.0);
+#if B200E_SOLVER == 2
+    L.wcur = R_(0.0);
+#endif
     L.state = LANE_EMPTY; L.failed = 0;
     L.nf0 = 0; L.nacc = 0; L.nrej = 0; L.ksave = 0;
     double wgt = 1.0;
@@ -595,7 +779,7 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 if (!repro) emit<REDUCE>(P, cur, L.u, L.p, wgt, A);
 #endif
                 if (!REDUCE && P.steps) P.steps[cur] = (int)(L.nacc + L.nrej);
-                A.count(L.nf0 + 6u * (L.nacc + L.nrej), L.nacc, L.nrej, L.failed ? 1u : 0u);
+                A.count(L.nf0 + NF_PER_ATTEMPT * (L.nacc + L.nrej), L.nacc, L.nrej, L.failed ? 1u : 0u);
                 L.state = LANE_EMPTY;
             }
             if (repro) {
@@ -641,7 +825,11 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 cur = next;
                 next = dyn ? P.npts : next + T;
                 L.nf0 = 0; L.nacc = 0; L.nrej = 0; L.failed = 0;
+#if B200E_SOLVER == 2
+                start_trajectory<GEN>(P, cur, L, wgt);
+#else
                 start_trajectory<GEN>(P, cur, L.u, L.p, L.k1, L.t, L.dt, L.le2old, wgt, L.nf0);
+#endif
                 L.state = (L.t < t1) ? LANE_ACTIVE : LANE_DONE;
 #if B200E_NSAVE > 0
                 // save times at t0 hold the initial state (save_start)
@@ -654,7 +842,11 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
         if (act_m == 0u) continue;
         // ---- step phase: a tight loop, one vote per step, until some lane finishes ----
         do {
+#if B200E_SOLVER == 2
+            if (L.state == LANE_ACTIVE) lamba_step<REDUCE>(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps);
+#else
             if (L.state == LANE_ACTIVE) tsit5_step<REDUCE>(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps, SaveCtx{P, cur, wgt, A});
+#endif
         } while (__ballot_sync(B200E_FULL, L.state == LANE_ACTIVE) == act_m);
     }
     block_reduce_store<REDUCE>(P, A);

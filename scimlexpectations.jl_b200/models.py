@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import math
 
-from ._capi import (ModelSpec, PDF_TRUNCNORMAL, PDF_UNIFORM, SOLVER_EM, SOLVER_TSIT5)
+from ._capi import (ModelSpec, PDF_TRUNCNORMAL, PDF_UNIFORM, SOLVER_EM, SOLVER_LAMBA_EM, SOLVER_TSIT5)
 
 # ---- reusable pieces: the structured h / g forms the Julia shim recognises (SURVEY.md hard part 8) ----
 
@@ -192,6 +192,12 @@ def gbm4(**kw) -> ModelSpec:
                      pdf=list(_KKL8_PDF)).replace(**kw)
 
 
+def gbm4_lamba(**kw) -> ModelSpec:
+    """test/processnoise.jl:9-15 as the reference runs it: ProcessNoiseSystemMap(prob, 8, LambaEM(),
+    abstol = 1e-3, reltol = 1e-3) -- the adaptive solver instead of north_star's fixed-step Euler-Maruyama."""
+    return gbm4(solver=SOLVER_LAMBA_EM, abstol=1e-3, reltol=1e-3, dt_fixed=0.0).replace(**kw)
+
+
 # ---- a larger state: radioactive-decay chain u_0 -> u_1 -> ... -> u_7 with uncertain rates (synthetic; exercises
 # the register budget: 8 states x 7 stages do not fit 128 registers) ----
 def decay_chain8(**kw) -> ModelSpec:
@@ -211,6 +217,7 @@ BUILTIN = {
     "decay1": decay1,
     "oscillator_noise": oscillator_noise,
     "gbm4": gbm4,
+    "gbm4_lamba": gbm4_lamba,
     "linear2_saveat": linear2_saveat,
     "growth_saveat": growth_saveat,
     "decay_chain8": decay_chain8,
@@ -221,4 +228,4 @@ def builtin(name: str, **kw) -> ModelSpec:
     return BUILTIN[name](**kw)
 
 
-__all__ = ["BUILTIN", "builtin", "hmap_scatter", "observable_components", "SOLVER_TSIT5", "SOLVER_EM"] + list(BUILTIN)
+__all__ = ["BUILTIN", "builtin", "hmap_scatter", "observable_components", "SOLVER_TSIT5", "SOLVER_EM", "SOLVER_LAMBA_EM"] + list(BUILTIN)

@@ -30,10 +30,13 @@ def main():
     with open(os.path.join(HERE, "readme_linear2.json"), "w") as f:
         json.dump(README, f, indent=1)
     out = {}
-    for name in ("linear2", "lotka_volterra", "lorenz63", "decay1", "oscillator_noise", "gbm4"):
-        n = 256 if name not in ("oscillator_noise", "gbm4") else 64
+    for name in ("linear2", "lotka_volterra", "lorenz63", "decay1", "oscillator_noise", "gbm4", "gbm4_lamba"):
+        n = 256 if name not in ("oscillator_noise", "gbm4", "gbm4_lamba") else 64
         x = sample_points(name, n, seed=11)
-        orc = oracle.OracleProblem.builtin(name)
+        if name == "gbm4_lamba":  # test/processnoise.jl:15: LambaEM(), abstol = reltol = 1e-3
+            orc = oracle.OracleProblem.builtin("gbm4", solver=oracle.SOLVER_LAMBA_EM, abstol=1e-3, reltol=1e-3)
+        else:
+            orc = oracle.OracleProblem.builtin(name)
         dx, c, steps = orc.eval_nodes(x, weight_by_pdf=True, want_steps=True)
         s, s2, c2 = orc.reduce_samples(x, weight_by_pdf=False)
         out[f"{name}_x"] = x

@@ -19,6 +19,7 @@ DISTS = {
     "decay1": [("tn", 0.5, 1.5, 1.0, 0.1)],
     "oscillator_noise": [("tn", -4.0, 4.0, 0.0, 1.0)] * 8,
     "gbm4": [("tn", -4.0, 4.0, 0.0, 1.0)] * 8,
+    "gbm4_lamba": [("tn", -4.0, 4.0, 0.0, 1.0)] * 8,
     "linear2_saveat": [("u", 1.0, 10.0), ("tn", 0.0, 6.0, 3.0, 1.0)],
     "growth_saveat": [("u", 0.0, 10.0)],
     "decay_chain8": [("u", 0.5 + 0.1 * i, 1.5 + 0.1 * i) for i in range(8)],
@@ -65,6 +66,8 @@ def oracle_for(name, **kw):
     spec = sme.models.builtin(name)
     if not len(spec.save_times) and name in ("linear2", "lotka_volterra", "lorenz63", "decay1", "oscillator_noise", "gbm4"):
         return oracle.OracleProblem.builtin(name, **kw)
+    opts = dict(abstol=spec.abstol, reltol=spec.reltol) if spec.solver != sme.models.SOLVER_EM else dict(dt_fixed=spec.dt_fixed)
+    opts.update(kw)
     return oracle.OracleProblem.from_source(spec.source, nstate=spec.nstate, nparam=spec.nparam, nx=spec.nx, nout=spec.nout,
-                                            u0=spec.u0, p=spec.p, tspan=spec.tspan, pdf=spec.pdf,
-                                            save_times=spec.save_times, **kw)
+                                            u0=spec.u0, p=spec.p, tspan=spec.tspan, pdf=spec.pdf, solver=spec.solver,
+                                            n_kkl=spec.n_kkl, save_times=spec.save_times, **opts)
