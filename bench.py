@@ -37,8 +37,17 @@ WORKLOADS = {
     "lorenz63_mc": ("lorenz63", 16_000_000, "Lorenz-63, 3 uncertain params + 3 uncertain u0, MonteCarlo block of 1.6e7 (C4 streams 10^9 in such blocks)"),
     "lotka_volterra_mc": ("lotka_volterra", 8_000_000, "Lotka-Volterra 4 uncertain params, MonteCarlo(8e6)"),
     "oscillator_noise_mc": ("oscillator_noise", 2_000_000, "KKL process-noise damped oscillator, Euler-Maruyama dt=2^-10, MonteCarlo(2e6)"),
+    "gbm4_lamba_mc": ("gbm4_lamba", 2_000_000, "test/processnoise.jl:9-15: du = u dt + u dW, 8-term KKL noise, adaptive LambaEM abstol=reltol=1e-3, MonteCarlo(2e6)"),
 }
-F_RHS = {"linear2": 6, "lotka_volterra": 6, "lorenz63": 8, "decay1": 1, "oscillator_noise": 7, "gbm4": 0}
+F_RHS = {"linear2": 6, "lotka_volterra": 6, "lorenz63": 8, "decay1": 1, "oscillator_noise": 7, "gbm4": 0, "gbm4_lamba": 0}
+
+
+def oracle_problem(model: str, **kw):
+    """The CPU restatement of a bench model (test infrastructure, used by the cpu_baseline / reference legs only)."""
+    import oracle
+    if model == "gbm4_lamba":
+        return oracle.OracleProblem.builtin("gbm4", solver=oracle.SOLVER_LAMBA_EM, abstol=1e-3, reltol=1e-3, **kw)
+    return oracle.OracleProblem.builtin(model, **kw)
 
 
 def algorithmic_flops(model: str, spec, counters: dict, npts: int) -> float:
@@ -47,6 +56,12 @@ def algorithmic_flops(model: str, spec, counters: dict, npts: int) -> float:
     if spec.solver == 0:
         att = counters["naccept"] + counters["nreject"]
         return counters["nf"] * F_RHS[model] + att * (70 * n + 12) + npts * (12 * n + 10) + npts * spec.nout
+    if spec.solver == 2:
+        # LambaEM: per attempted step two drift + two diffusion evaluations, 16n for K, u', utilde, Ed, En, the
+        # scaled residual and its square sum, 3*n_kkl for W(t+dt) (each sine counted as 1, like each pow) and the
+        # 12 of the controller
+        att = counters["naccept"] + counters["nreject"]
+        return att * (4 * F_RHS[model] + 16 * n + 3 * spec.n_kkl + 12) + npts * (12 * n + 10) + npts * spec.nout
     # Euler-Maruyama: per step 2*n_kkl (dW from the table) + F_f + F_g + 4n
     return counters["naccept"] * (2 * spec.n_kkl + F_RHS[model] + 4 * n) + npts * spec.nout
 
@@ -122,8 +137,7 @@ def host_cores() -> int:
 def cpu_restatement_rate(model: str, n_sample: int, seed: int = 7, reps: int = 1, x=None):
     """Times the oracle (CPU restatement of the reference path) on all host cores.  Returns
     (evals/s, cores, n, seconds)."""
-    import oracle
-    orc = oracle.OracleProblem.builtin(model)
+    orc = oracle_problem(model)
     cores = host_cores()
     if x is None:
         x = np.empty((n_sample, orc.nx))
@@ -193,8 +207,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     model, n_full, desc = WORKLOADS[args.workload]
-    import oracle
-    orc = oracle.OracleProblem.builtin(model)
+    orc = oracle_problem(model)
     cores = host_cores()
     # bounded sample per step: ~2 s of CPU work, calibrated on a small block
     x_cal = np.empty((1 << 17, orc.nx))

@@ -13,6 +13,8 @@
 #                                                        (reference src/expectation.jl:268-294)
 #     solve(::ExpectationProblem{<:SystemMap{..,EnsembleB200}}, ::Koopman, ::B200Cubature)   (optional: the whole
 #                                                        h-adaptive solve as one C call, src/expectation.jl:336-354)
+#     the same two methods for ExpectationProblem{<:ProcessNoiseSystemMap} whose forwarded solve arguments are
+#     (EM() | LambaEM(), EnsembleB200(...))             (reference src/expectation.jl:209-249, :295-325)
 # so that `solve(exprob, Koopman(); batch=..., quadalg=CubatureJLh())` and `solve(exprob, MonteCarlo(n))`
 # keep their signatures.  Julia closures cannot run on the device: f, g, h travel as CUDA source
 # (fields of `B200Model`); `h`/`g` of the structured forms (scatter x into u0/p, end-state components)
@@ -54,6 +56,7 @@ Base.@kwdef struct B200Model
     hmap::String                     # B200E_FN void hmap(const real* x, const real* u0n, const real* pn, real* u0, real* p)
     observable::String               # B200E_FN void observable(const real* u_end, const real* p, real t_end, real* out)
     nout::Int
+    diffusion::String = ""           # process noise only: B200E_FN void diffusion(real* g, const real* u, const real* p, real t)
 end
 
 Base.@kwdef struct EnsembleB200 <: SciMLBase.EnsembleAlgorithm
@@ -77,21 +80,23 @@ check(rc, h) = rc == 0 ? nothing :
     error("libb200expect: ", unsafe_string(ccall((:b200e_last_error, LIB), Cstring, (Ptr{Cvoid},), h)), " (status $rc)")
 
 "b200e_create for `exprob` (factors of the product density come from the keyword `dists`)."
-function create_handle(exprob::ExpectationProblem, dists)
-    S = exprob.S; prob = S.prob; ens = S.ensemblealg; m = ens.model
-    u0 = collect(Float64, prob.u0); p = collect(Float64, prob.p)
+create_handle(exprob::ExpectationProblem, dists) =
+    create_handle(exprob.S.prob, exprob.S.ensemblealg, exprob.S.kwargs, dists)
+function create_handle(prob, ens::EnsembleB200, kw, dists; solver = 0, n_kkl = 0, dt_fixed = 0.0,
+                       default_tol = (1e-6, 1e-3))
+    m = ens.model
+    u0 = collect(Float64, prob.u0); p = collect(Float64, prob.p === nothing || prob.p isa SciMLBase.NullParameters ? Float64[] : prob.p)
     pdf = PdfDim[pdfdim(d) for d in dists]
-    src = m.rhs * "\n" * m.hmap * "\n" * m.observable
-    kw = S.kwargs
+    src = m.rhs * "\n" * m.diffusion * "\n" * m.hmap * "\n" * m.observable
     # saveat of the ODEProblem (docs/src/tutorials/introduction.md:207-212): the observable is then an
     # `observable_at(k, t, u, p, out)` source and nout = length(saveat) * outputs per save time
     saves = collect(Float64, get(prob.kwargs, :saveat, Float64[]))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve u0 p pdf src ens saves begin
-        cm = CModel(sizeof(CModel), length(u0), length(p), length(pdf), m.nout, 0, 0, ens.fp32 ? 1 : 0,
+        cm = CModel(sizeof(CModel), length(u0), length(p), length(pdf), m.nout, solver, n_kkl, ens.fp32 ? 1 : 0,
                     Base.unsafe_convert(Cstring, src), pointer(u0), pointer(p),
-                    prob.tspan[1], prob.tspan[2], get(kw, :abstol, 1e-6), get(kw, :reltol, 1e-3),
-                    get(kw, :dtmax, 0.0), 0.0, get(kw, :maxiters, 100000), pointer(pdf),
+                    prob.tspan[1], prob.tspan[2], get(kw, :abstol, default_tol[1]), get(kw, :reltol, default_tol[2]),
+                    get(kw, :dtmax, 0.0), dt_fixed, get(kw, :maxiters, 100000), pointer(pdf),
                     length(ens.devices), isempty(ens.devices) ? Ptr{Int32}(C_NULL) : pointer(ens.devices),
                     0, 0, 0, 0, ens.schedule, length(saves), isempty(saves) ? Ptr{Float64}(C_NULL) : pointer(saves),
                     Cstring(C_NULL))
@@ -172,6 +177,56 @@ function SciMLBase.solve(exprob::B200Problem, expalg::MonteCarlo; dists = exprob
     return ExpectationSolution(nout == 1 ? u[1] : u, nothing, nothing)
 end
 
+# ---- process noise (reference src/expectation.jl:209-249 Koopman, :295-325 MonteCarlo) ----------------
+# ProcessNoiseSystemMap(prob, n, args...; kwargs...) forwards `args` to solve (src/system_utils.jl:98-100), so the
+# ensemble algorithm is its second positional argument:  ProcessNoiseSystemMap(prob, 8, LambaEM(), EnsembleB200(...);
+# abstol = 1e-3, reltol = 1e-3)  (test/processnoise.jl:15 plus the ensemble slot).  Dispatch is on the type of `args`.
+import SciMLExpectations: ProcessNoiseSystemMap
+const B200NoiseMap = ProcessNoiseSystemMap{<:Any, <:Tuple{Any, EnsembleB200}}
+const B200NoiseProblem = ExpectationProblem{<:B200NoiseMap}
+
+function create_noise_handle(exprob::B200NoiseProblem, dists)
+    S = exprob.S; alg, ens = S.args
+    name = string(nameof(typeof(alg)))
+    if name == "LambaEM"                                   # adaptive: SciML's SDE default tolerances are 1e-2 / 1e-2
+        return create_handle(S.prob, ens, S.kwargs, dists; solver = 2, n_kkl = S.n, default_tol = (1e-2, 1e-2))
+    elseif name == "EM"                                    # fixed step: solve(...; dt = ...)
+        return create_handle(S.prob, ens, S.kwargs, dists; solver = 1, n_kkl = S.n, dt_fixed = Float64(S.kwargs[:dt]))
+    end
+    error("B200Expectations: the process-noise path carries EM() and LambaEM(), not $name")
+end
+
+function build_integrand(prob::B200NoiseProblem, ::Koopman, mid, p, batch::Integer; dists = prob.d.pdf_func.dists)
+    h = create_noise_handle(prob, dists)
+    nout = prob.S.args[2].model.nout
+    function integrand_koopman_processnoisesystemmap_batch!(dx, x, _)
+        check(ccall((:b200e_eval_nodes, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Float64}),
+                    h, x, size(x)[end], 0, 1, dx), h)     # Z = x[:, i]; g(sol, p) * pdf(d, x[:, i])  (:227)
+        return nothing
+    end
+    prototype = nout == 1 ? zeros(1) : zeros(nout, 1)
+    integrand_koopman_processnoisesystemmap_batch!(prototype, reshape(collect(mid), size(mid)..., 1), p)   # :245
+    return BatchIntegralFunction{true}(integrand_koopman_processnoisesystemmap_batch!, prototype; max_batch = batch)
+end
+
+function SciMLBase.solve(exprob::B200NoiseProblem, expalg::MonteCarlo; dists = exprob.d.pdf_func.dists)
+    h = create_noise_handle(exprob, dists)
+    ens = exprob.S.args[2]; nout = ens.model.nout; n = expalg.trajectories
+    s = zeros(nout); s2 = zeros(nout); c = Ref(Counters(0, 0, 0, 0))
+    check(ccall((:b200e_reduce_generated, LIB), Cint,     # Z = rand(d) drawn in the kernel (:305), weight 1
+                (Ptr{Cvoid}, UInt64, UInt64, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Counters}),
+                h, ens.seed, 0, n, s, s2, c), h)
+    c[].nfail > 0 && @warn "libb200expect: $(c[].nfail) trajectories aborted (maxiters / non-finite / dt underflow)"
+    ccall((:b200e_destroy, LIB), Cint, (Ptr{Cvoid},), h)
+    u = s ./ n                                             # mean(sol.u), :324
+    return ExpectationSolution(nout == 1 ? u[1] : u, nothing, nothing)
+end
+
+hmap_noise(n) =                                                 # cov(x, u, p) = x, p  (test/processnoise.jl:16): Z = x
+    "B200E_FN void hmap(const real* x, const real* u0_nom, const real* p_nom, real* z, real* p) {\n" *
+    join(["  z[$(k-1)] = x[$(k-1)];\n" for k in 1:n]) * "}\n"
+
 # ---- structured h / g source generators --------------------------------------------------------------
 hmap_scatter(; u0 = Pair{Int,Int}[], p = Pair{Int,Int}[]) =     # u0 = [i => j]: u0[i] = x[j]  (1-based in, 0-based out)
     "B200E_FN void hmap(const real* x, const real* u0_nom, const real* p_nom, real* u0, real* p) {\n" *
@@ -184,5 +239,5 @@ observable_at_components(idx) =                                 # g(sol,p) = sol
     "B200E_FN void observable_at(int k, real t, const real* u, const real* p, real* out) {\n" *
     join(["  out[$(j-1)] = u[$(i-1)];\n" for (j, i) in enumerate(idx)]) * "}\n"
 
-export EnsembleB200, B200Model, B200Cubature, hmap_scatter, observable_components, observable_at_components
+export EnsembleB200, B200Model, B200Cubature, hmap_scatter, hmap_noise, observable_components, observable_at_components
 end # module

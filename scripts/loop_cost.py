@@ -7,7 +7,7 @@ pat = sys.argv[1] if len(sys.argv) > 1 else "du[1] = -u[0]"
 show = len(sys.argv) > 2 and sys.argv[2] == "show"
 for cu in sorted(glob.glob(cache + "/*.cu")):
     t = open(cu).read()
-    if not (pat in t and "#define B200E_FP32 0" in t and "#define B200E_SOLVER 0" in t):
+    if not (pat in t and "#define B200E_FP32 0" in t and ("#define B200E_SOLVER 0" in t or "#define B200E_SOLVER 2" in t)):
         continue
     mb = re.search(r"#define B200E_MINBLOCKS (\d+)", t).group(1)
     cubin = cu[:-3] + ".cubin"

@@ -197,3 +197,21 @@ def test_lamba_through_the_mirrored_api_and_fp32(gpu):
     sol32 = gpu.solve(ex32, gpu.MonteCarlo(100000, seed=5))
     assert np.allclose(sol32.u, sol.u, rtol=2e-3)
     ex.close(); ex32.close()
+
+
+@pytest.mark.gpu
+def test_reference_processnoise_testset_koopman_vs_montecarlo(gpu):
+    """reference test/processnoise.jl:9-26 end to end: Koopman (ireltol = iabstol = 1e-3) against
+    MonteCarlo(1_000_000), both with LambaEM(abstol = reltol = 1e-3), must agree at rtol = 1e-2.  The reference
+    integrates with CubaDivonne; here the 8-dimensional integral goes through the h-adaptive Genz-Malik rule on
+    the device (401 nodes per region), which needs more than the reference's default 1e6 evaluations."""
+    m = gpu.models
+    prob = gpu.SDEProblem(m._GBM, "", [1.0, 2.0, 3.0, 4.0], (0.0, 1.0))
+    sm = gpu.ProcessNoiseSystemMap(prob, 8, gpu.LambaEM(), abstol=1e-3, reltol=1e-3)
+    ex = gpu.ExpectationProblem(sm, m.observable_components([0, 1, 2, 3]), m.hmap_scatter(z_from_x=[(k, k) for k in range(8)]), nout=4)
+    sol1 = gpu.solve(ex, gpu.Koopman(), ireltol=1e-3, iabstol=1e-3, batch=64, quadalg=gpu.B200Cubature(), maxiters=40_000_000)
+    sol2 = gpu.solve(ex, gpu.MonteCarlo(1_000_000))
+    assert np.allclose(sol1.u, sol2.u, rtol=1e-2), (sol1.u, sol2.u)     # the reference's own assertion
+    st = sol1.original
+    assert st["counters"]["nfail"] == 0 and st["nevals"] >= 1_000_000
+    ex.close()
