@@ -501,7 +501,7 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
 //   EEst = RMS_i( (|Ed_i| + |En_i|) / (abstol + max(|u_i|,|u'_i|) reltol) )
 //   beta1 = 7/10, beta2 = 2/5, gamma = 9/10, qmin = 1/5, qmax = 1.125, qoldinit = 1e-4.
 // W(t) = sum_k Z_k sqrt(2) sin((k-1/2) pi t) / ((k-1/2) pi) is needed at arbitrary t here (no table as in
-// the fixed-step kernel): ONE sincospi and the three-term recurrence
+// the fixed-step kernel): ONE sine (sin_halfpi, 15 FP64 instructions) and the three-term recurrence
 //   s_{k+1} = 2 cos(pi t) s_k - s_{k-1},  s_k = sin((k-1/2) pi t),  s_0 = -s_1
 // give all NK modes in 2 DFMAs each; the reference evaluates NK sines per query (src/expectation.jl:217-220).
 // ------------------------------------------------------------------------------------------
@@ -524,12 +524,7 @@ struct SaveCtx {
 };
 
 __device__ __forceinline__ real kkl_w(const real *zc, const real t) {
-    real s, c;
-#if B200E_FP32
-    sincospif(R_(0.5) * t, &s, &c);
-#else
-    sincospi(R_(0.5) * t, &s, &c);
-#endif
+    const real s = sin_halfpi(t);
     const real c2 = fma(R_(-4.0) * s, s, R_(2.0));  // 2 cos(pi t) = 2 - 4 sin^2(pi t / 2)
     real sp = -s, sk = s, w = R_(0.0);
 #pragma unroll
@@ -642,7 +637,7 @@ __device__ __forceinline__ void lamba_step(Lane &L, const real t1, const real dt
     // PI controller in log space on e2 (see tsit5_step): EEst^b1 = e2^(b1/2)
     const real le2 = log_pos(sh_tab, e2);
     const real hist = accept ? L.le2old : R_(0.0);
-    real qinv = exp_small(sh_tab, fma(R_(0.2), hist, fma(R_(-0.35), le2, K_(ln_gamma))));  // gamma qold^b2 / EEst^b1
+    real qinv = exp_small(sh_tab, fma(K_(sde_hb2), hist, fma(-K_(sde_hb1), le2, K_(ln_gamma))));  // gamma qold^b2 / EEst^b1
     qinv = pmin(R_(1.125), pmax(K_(qmin), qinv));
     L.dt = dt * qinv;
 #if B200E_CLIP_DTMAX

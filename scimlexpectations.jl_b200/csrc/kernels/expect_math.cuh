@@ -72,6 +72,13 @@ constexpr double ln10_04 = 0.4 * 2.302585092994045684;
 // series coefficients rounded to the 21 bits a DFMA immediate carries.  Their terms are at most
 // 2^-24 (log: r^3/3, |r| <= 2^-8) resp. 2^-27 (exp: r^3/6, |r| <= 2^-8.5) of the result, so the
 // 2^-21 rounding stays below 2^-45 * 2^-8 ... i.e. under 1e-14 absolute; they cost no register.
+// LambaEM (expect_kernels.cuh): SDE PI-controller exponents on e2 (beta1/2, beta2/2) and the Taylor coefficients of
+// sin(pi r / 2) = r (sp0 + r^2 (sp1 + ... + r^2 sp10)), |r| <= 1 (next term 1.3e-18)
+constexpr double sde_hb1 = 0.5 * 7.0 / 10.0, sde_hb2 = 0.5 * 2.0 / 5.0;
+constexpr double sp0 = 1.5707963267948966192, sp1 = -0.64596409750624625366, sp2 = 0.079692626246167045121,
+                 sp3 = -0.0046817541353186881007, sp4 = 0.00016044118478735982187, sp5 = -3.5988432352120853405e-6,
+                 sp6 = 5.6921729219679268118e-8, sp7 = -6.6880351098114672325e-10, sp8 = 6.0669357311061956671e-12,
+                 sp9 = -4.3770654673137422772e-14, sp10 = 2.5714228928604738662e-16;
 constexpr double third_i = 0x1.55555p-2, fifth_i = 0x1.9999ap-3;
 constexpr double sixth_i = 0x1.55555p-3, r24_i = 0x1.55555p-5;
 }  // namespace lit
@@ -84,6 +91,7 @@ struct b200e_consts {
         a72, a73, a74, a75, a76, bt1, bt2, bt3, bt4, bt5, bt6, bt7;
     double hb1, hb2, ln_gamma, qmin, qmax, le2_qoldinit, inv_n;
     double ln2, log2e_128, ln2_128, ln10_04, fifth, r24;
+    double sde_hb1, sde_hb2, sp0, sp1, sp2, sp3, sp4, sp5, sp6, sp7, sp8, sp9, sp10;
 };
 // not `const`: the compiler must read it from the constant bank instead of folding literals back in
 B200E_CONST b200e_consts KC = {
@@ -91,7 +99,9 @@ B200E_CONST b200e_consts KC = {
     lit::a52, lit::a53, lit::a54, lit::a61, lit::a62, lit::a63, lit::a64, lit::a65, lit::a71, lit::a72, lit::a73,
     lit::a74, lit::a75, lit::a76, lit::bt1, lit::bt2, lit::bt3, lit::bt4, lit::bt5, lit::bt6, lit::bt7,
     lit::hb1, lit::hb2, lit::ln_gamma, lit::qmin, lit::qmax, lit::le2_qoldinit, lit::inv_n,
-    lit::ln2, lit::log2e_128, lit::ln2_128, lit::ln10_04, 0.2, 1.0 / 24.0};
+    lit::ln2, lit::log2e_128, lit::ln2_128, lit::ln10_04, 0.2, 1.0 / 24.0,
+    lit::sde_hb1, lit::sde_hb2, lit::sp0, lit::sp1, lit::sp2, lit::sp3, lit::sp4, lit::sp5, lit::sp6, lit::sp7, lit::sp8,
+    lit::sp9, lit::sp10};
 #define K_(name) (KC.name)
 #endif
 
@@ -122,11 +132,13 @@ B200E_MFN float log_pos(const b200e_tabs &, float x) {
 }
 B200E_MFN float exp_small(const b200e_tabs &, float y) { return __expf(y); }
 B200E_MFN float sqrt_pos(float x) { return __fsqrt_rn(x); }
+B200E_MFN float sin_halfpi(float t) { return sinpif(0.5f * t); }
 #else
 B200E_MFN float rcp_pos(float b) { return 1.0f / b; }
 B200E_MFN float log_pos(const b200e_tabs &, float x) { return logf(x); }
 B200E_MFN float exp_small(const b200e_tabs &, float y) { return expf(y); }
 B200E_MFN float sqrt_pos(float x) { return sqrtf(x); }
+B200E_MFN float sin_halfpi(float t) { return sinf(1.5707963267948966f * t); }
 #endif
 #else
 // 1/b for normal b > 0: MUFU.RCP64H seed (20 bits: it reads the high word only) + one cubic step
@@ -194,6 +206,29 @@ B200E_MFN double exp_small(const b200e_tabs &T, double y) {
     h = fma(h, r, 1.0);
     const double p = fma(tj * h, r, tj);
     return __hiloint2double(__double2hiint(p) + ((n >> TAB_BITS) << 20), __double2loint(p));
+}
+// sin(pi t / 2) for |t| < 2^50, the one transcendental of the KKL noise path (LambaEM evaluates W(t) at arbitrary
+// t): n = round(t / 2), r = t - 2 n in [-1, 1] (exact), sin(pi t / 2) = (-1)^n sin(pi r / 2) by an odd Taylor
+// polynomial of degree 21 -- 15 FP64 instructions, every coefficient a constant-bank operand, the sign applied on
+// the integer pipe.  Absolute error below 3e-16 (tests/test_device_math.py).  CUDA's sincospi costs about twice
+// that in FP64 instructions plus two moves per 64-bit literal coefficient.
+B200E_MFN double sin_halfpi(double t) {
+    const double m = fma(t, 0.5, lit::rnd_magic);
+    const int n = __double2loint(m);
+    const double r = fma(m - lit::rnd_magic, -2.0, t);
+    const double r2 = r * r;
+    double h = fma(r2, K_(sp10), K_(sp9));
+    h = fma(h, r2, K_(sp8));
+    h = fma(h, r2, K_(sp7));
+    h = fma(h, r2, K_(sp6));
+    h = fma(h, r2, K_(sp5));
+    h = fma(h, r2, K_(sp4));
+    h = fma(h, r2, K_(sp3));
+    h = fma(h, r2, K_(sp2));
+    h = fma(h, r2, K_(sp1));
+    h = fma(h, r2, K_(sp0));
+    const double s = h * r;
+    return __hiloint2double(__double2hiint(s) ^ (int)((unsigned)n << 31), __double2loint(s));
 }
 #endif
 

@@ -74,6 +74,8 @@ def test_compile_check_all_builtin_models_for_sm100a(sme, tmp_path):
             # the library picks the densest residency (4 / 3 / 2 blocks of 256) within its 32-byte spill allowance;
             # a system too large for 128 registers (8 states in FP64) stays at two blocks and spills into L1
             allowance = 32 if spec.nstate * (1 if fp else 2) < 16 else 512
+            if spec.solver == sme.models.SOLVER_LAMBA_EM:
+                allowance = 64   # measured: three blocks with up to 52 B of spills beat two blocks without (DESIGN K8)
             assert len(spills) == 5 and max(spills) <= allowance, (name, fp, spills)   # nodes / reduce x static / dynamic + reduce_gen
             # second call is served from the cubin cache
             n2, log2 = sme.compile_check(spec)

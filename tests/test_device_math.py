@@ -45,6 +45,27 @@ int main() {
     printf("%.3e %.3e %.3e %.3e %.3e\n", maxl, maxe, maxr, maxs, maxpow);
     const double sp[] = {0.0, 4.9e-324, 1e-310, 1e308, INFINITY, NAN, -NAN, -1.0};
     for (double x : sp) printf("%.6f\n", log_pos(T, x));
+    // sin(pi t / 2) of the LambaEM noise path against libm, and the recurrence s_{k+1} = 2 cos(pi t) s_k - s_{k-1}
+    // for sin((k - 1/2) pi t), k <= 32, built on it (expect_kernels.cuh kkl_w)
+    double maxsin = 0, maxrec = 0;
+    for (int i = 0; i < 2000000; i++) {
+        const double t = std::uniform_real_distribution<double>(-3, 40)(g);
+        const double s = sin_halfpi(t);
+        maxsin = std::fmax(maxsin, std::fabs(s - std::sin(1.5707963267948966192 * t)));
+        if (i % 16 == 0) {
+            const double c2 = fma(-4.0 * s, s, 2.0);
+            double sp_ = -s, sk = s;
+            for (int k = 1; k <= 32; k++) {
+                maxrec = std::fmax(maxrec, std::fabs(sk - std::sin((k - 0.5) * 3.14159265358979323846 * t)));
+                const double sn = fma(c2, sk, -sp_);
+                sp_ = sk;
+                sk = sn;
+            }
+        }
+    }
+    printf("%.3e %.3e\n", maxsin, maxrec);
+    const double ex[] = {0.0, 1.0, 2.0, 3.0, -1.0, 0.5, 1e15};
+    for (double t : ex) printf("%.17g\n", sin_halfpi(t));
     return 0;
 }
 """
@@ -79,3 +100,15 @@ def test_log_is_finite_and_saturates_for_special_values(twin):
     # patterns -> about +707 (clamps to the reject factor qmin): the kernel needs no special case
     assert all(v < -700 for v in vals[:3])
     assert all(v > 700 for v in vals[3:])
+
+
+def test_sin_halfpi_and_the_kkl_recurrence(twin):
+    """The one sine of the adaptive process-noise path (K8) and the three-term recurrence that turns it into all
+    KKL modes: absolute errors against libm (whose own argument pi t / 2 is rounded: ~4e-15 at t = 40)."""
+    maxsin, maxrec = (float(v) for v in twin[9].split())
+    assert maxsin < 8e-15
+    assert maxrec < 2e-11      # 32 modes; the recurrence amplifies by ~k^2 near t = even integers
+    exact = [float(v) for v in twin[10:17]]
+    want = [0.0, 1.0, 0.0, -1.0, -1.0, 2 ** -0.5]     # t = 0, 1, 2, 3, -1, 1/2: zeros are exact
+    assert exact[0] == 0.0 and exact[2] == 0.0 and all(abs(a - b) < 2.3e-16 for a, b in zip(exact, want))
+    assert abs(exact[6]) <= 1.0                        # t = 1e15: still a sine
