@@ -7,13 +7,13 @@ import scimlexpectations_jl_b200 as sme
 from tests.sampling_util import sample_points
 nd = sme.device_count()
 for devices in ([0],) + (([0, 1],) if nd >= 2 else ()):
-    for name in ("linear2", "lotka_volterra", "oscillator_noise", "linear2_saveat"):
+    for name in ("linear2", "lotka_volterra", "oscillator_noise", "linear2_saveat", "gbm4_lamba"):
         for fp in (0, 1):
             ref = None
             for sched in (0, 1, 2):
                 if sched == 2 and name == "linear2_saveat":
                     continue
-                n = 20011 if name != "oscillator_noise" else 3001
+                n = 20011 if name not in ("oscillator_noise", "gbm4_lamba") else 3001
                 x = sample_points(name, n, seed=1)
                 with sme.Handle(sme.models.builtin(name, schedule=sched, fp_mode=fp, block_size=64, blocks_per_sm=1, devices=devices,
                                                    chunk_points=7000)) as h:

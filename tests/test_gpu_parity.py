@@ -714,3 +714,18 @@ def test_split_reduce_call(gpu):
         assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
         assert h.last_stats()["kernel_ms"] > 0
         d.free()
+
+
+@pytest.mark.parametrize("seed", [0, 5, 8])
+def test_random_models_match_oracle(gpu, seed):
+    """Differential test on generated models (tests/fuzz_util.py; scripts/fuzz_parity.py runs many more seeds):
+    random dissipative systems of 1-5 states with a nonlinearity, random h (x into u0 and / or p), random
+    product densities (uniform / truncated normal / normal), end-state or time-sampled observables, random
+    tolerances, schedules, layouts, batch sizes from 1 point to several launches' worth."""
+    from tests.fuzz_util import compare, oracle_of, random_model
+    spec, draw = random_model(seed)
+    orc = oracle_of(spec)
+    rng = np.random.default_rng([7, seed])
+    with gpu.Handle(spec) as h:
+        for n in (1, 97, 20011):
+            compare(h, spec, orc, draw(n, n), int(rng.integers(0, 2)), bool(rng.integers(0, 2)))
