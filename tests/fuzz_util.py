@@ -17,10 +17,11 @@ def _lit(v):
     return f"B200E_REAL({float(v)!r})"
 
 
-def random_model(seed: int):
-    """Returns (spec, draw) with draw(n, seed) -> (n, nx) samples of the model's own density."""
-    rng = np.random.default_rng([20261020, seed])
-    n = int(rng.integers(1, 6))
+def random_model(seed: int, nmax: int = 5):
+    """Returns (spec, draw) with draw(n, seed) -> (n, nx) samples of the model's own density.  ``nmax`` > 5 draws
+    the large systems (6..nmax states) whose stages do not fit the register file."""
+    rng = np.random.default_rng([20261020, seed] + ([nmax] if nmax != 5 else []))
+    n = int(rng.integers(1, 6)) if nmax <= 5 else int(rng.integers(6, nmax + 1))
     m = int(rng.integers(0, 4))
     S = np.triu(rng.uniform(-1.5, 1.5, (n, n)), 1)
     A = S - S.T - np.diag(rng.uniform(0.2, 1.5, n))
@@ -95,11 +96,51 @@ def random_model(seed: int):
     return spec, draw
 
 
+def random_noise_model(seed: int):
+    """A process-noise model (src/expectation.jl:209-249 / :295-325): 1-4 states, random drift and diffusion
+    (zero / constant / linear / bounded-nonlinear per component), 1-13 KKL modes (odd and even counts), fixed-step
+    Euler-Maruyama or adaptive LambaEM; x = Z with the +-4 sigma truncated normals of problem_types.jl:83."""
+    rng = np.random.default_rng([20261021, seed])
+    n = int(rng.integers(1, 5))
+    nk = int(rng.choice([1, 2, 3, 5, 8, 13]))
+    S = np.triu(rng.uniform(-2.0, 2.0, (n, n)), 1)
+    A = S - S.T - np.diag(rng.uniform(0.1, 1.0, n))
+    fl, gl = [], []
+    for i in range(n):
+        terms = [f"{_lit(A[i, j])} * u[{j}]" for j in range(n) if A[i, j] != 0.0]
+        if rng.random() < 0.4:
+            terms.append(f"{_lit(rng.uniform(-0.5, 0.5))} * sin(u[{(i + 1) % n}] + t)")
+        fl.append(f"    du[{i}] = " + " + ".join(terms).replace("+ -", "- ") + ";")
+        kind = int(rng.integers(0, 4))
+        c = _lit(rng.uniform(0.2, 1.0))
+        gl.append(f"    g[{i}] = " + ["B200E_REAL(0.0)", c, f"{c} * u[{i}]", f"{c} * (B200E_REAL(1.0) + B200E_REAL(0.25) * cos(u[{i}]))"][kind] + ";")
+    src = ("B200E_FN void rhs(real* du, const real* u, const real* p, real t) {\n" + "\n".join(fl) + "\n}\n"
+           "B200E_FN void diffusion(real* g, const real* u, const real* p, real t) {\n" + "\n".join(gl) + "\n}\n")
+    src += sme.models.hmap_scatter(z_from_x=[(k, k) for k in range(nk)])
+    comps = sorted(rng.choice(n, size=int(rng.integers(1, n + 1)), replace=False).tolist())
+    src += sme.models.observable_components(comps)
+    adaptive = bool(rng.integers(0, 2))
+    tol = float(rng.choice([1e-2, 1e-3]))
+    pdf = [(PDF_TRUNCNORMAL, -4.0, 4.0, 0.0, 1.0)] * nk
+    spec = sme.ModelSpec(source=src, nstate=n, nparam=0, nx=nk, nout=len(comps), u0=rng.uniform(0.5, 1.5, n).tolist(), p=[],
+                         tspan=(0.0, float(rng.uniform(0.5, 1.5))), solver=2 if adaptive else 1, n_kkl=nk,
+                         abstol=tol, reltol=tol, dt_fixed=0.0 if adaptive else 2.0 ** -int(rng.integers(5, 10)),
+                         pdf=pdf, schedule=int(rng.integers(0, 3)))
+
+    def draw(npts: int, sseed: int = 0):
+        g = np.random.default_rng([seed, sseed, 1])
+        a, b = ndtr(-4.0), ndtr(4.0)
+        return np.clip(ndtri(a + (b - a) * g.random((npts, nk))), -4.0, 4.0)
+
+    return spec, draw
+
+
 def oracle_of(spec):
     import oracle
+    opts = dict(dt_fixed=spec.dt_fixed) if spec.solver == 1 else dict(abstol=spec.abstol, reltol=spec.reltol)
     return oracle.OracleProblem.from_source(spec.source, nstate=spec.nstate, nparam=spec.nparam, nx=spec.nx, nout=spec.nout,
                                             u0=spec.u0, p=spec.p, tspan=spec.tspan, pdf=spec.pdf, save_times=spec.save_times,
-                                            abstol=spec.abstol, reltol=spec.reltol)
+                                            solver=spec.solver, n_kkl=spec.n_kkl, **opts)
 
 
 def compare(h, spec, orc, x, layout: int, weight: bool):
