@@ -619,17 +619,19 @@ __device__ __forceinline__ void lamba_step(Lane &L, const real t1, const real dt
 #pragma unroll
     for (int i = 0; i < N; i++) un[i] = fma(Lg[i], dW, K[i]);
     rhs(f1, K, p, tnext);
-    const real sq = sqrt_pos(dt);
+    real sq, isq;
+    sqrt_rsqrt_pos(dt, sq, isq);
 #pragma unroll
     for (int i = 0; i < N; i++) v[i] = fma(Lg[i], sq, u[i]);
     diffusion(g1, v, p, t);
-    const real hdt = R_(0.5) * dt, hw = R_(0.5) * dW * dW * rcp_pos(sq);
+    const real hdt = R_(0.5) * dt, hw = R_(0.5) * dW * dW * isq;  // both >= 0
     real ss = R_(0.0);
 #pragma unroll
     for (int i = 0; i < N; i++) {
-        const real Ed = hdt * (f1[i] - f0[i]), En = (g1[i] - Lg[i]) * hw;
+        // |Ed| + |En| = |f1 - f0| dt/2 + |g1 - L| dW^2 / (2 sqrt(dt))
+        const real num = fma(abs_bits(g1[i] - Lg[i]), hw, abs_bits(f1[i] - f0[i]) * hdt);
         const real sc = fma(pmax(abs_bits(u[i]), abs_bits(un[i])), reltol, abstol);
-        const real r = (abs_bits(Ed) + abs_bits(En)) * rcp_pos(sc);
+        const real r = num * rcp_pos(sc);
         ss = fma(r, r, ss);
     }
     const real e2 = ss * R_(lit::inv_n);                // EEst^2

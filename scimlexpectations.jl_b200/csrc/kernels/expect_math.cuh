@@ -133,12 +133,14 @@ B200E_MFN float log_pos(const b200e_tabs &, float x) {
 B200E_MFN float exp_small(const b200e_tabs &, float y) { return __expf(y); }
 B200E_MFN float sqrt_pos(float x) { return __fsqrt_rn(x); }
 B200E_MFN float sin_halfpi(float t) { return sinpif(0.5f * t); }
+B200E_MFN void sqrt_rsqrt_pos(float x, float &s, float &rs) { s = __fsqrt_rn(x); rs = __frsqrt_rn(x); }
 #else
 B200E_MFN float rcp_pos(float b) { return 1.0f / b; }
 B200E_MFN float log_pos(const b200e_tabs &, float x) { return logf(x); }
 B200E_MFN float exp_small(const b200e_tabs &, float y) { return expf(y); }
 B200E_MFN float sqrt_pos(float x) { return sqrtf(x); }
 B200E_MFN float sin_halfpi(float t) { return sinf(1.5707963267948966f * t); }
+B200E_MFN void sqrt_rsqrt_pos(float x, float &s, float &rs) { s = sqrtf(x); rs = 1.0f / s; }
 #endif
 #else
 // 1/b for normal b > 0: MUFU.RCP64H seed (20 bits: it reads the high word only) + one cubic step
@@ -171,6 +173,25 @@ B200E_MFN double sqrt_pos(double x) {
     h = fma(h, r, h);
     const double d = fma(-g, g, x);
     return fma(d, h, g);
+}
+// sqrt(x) and 1/sqrt(x) together (the Goldschmidt iteration above carries both)
+B200E_MFN void sqrt_rsqrt_pos(double x, double &s, double &rs) {
+    double y;
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+    y = __hiloint2double(__double2hiint(1.0 / std::sqrt(__hiloint2double(__double2hiint(x), 0))), 0);
+#endif
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, x);
+    s = fma(d, h, g);
+    rs = h + h;  // 2 h -> 1/sqrt(x), relative error ~1e-16 after two coupled steps
 }
 // log(x), x > 0:  x = 2^e m, m in [1,2), j = top 7 bits of m's fraction;
 //   log x = e ln2 + lc_j + log1p(r),  r = x * (c_j 2^-e) - 1  (one exact-product DFMA), |r| <= 2^-8,

@@ -35,6 +35,9 @@ int main() {
         maxe = std::fmax(maxe, std::fabs(exp_small(T, y) / std::exp(y) - 1));
         maxr = std::fmax(maxr, std::fabs(rcp_pos(x) * x - 1));
         maxs = std::fmax(maxs, std::fabs(sqrt_pos(x) / std::sqrt(x) - 1));
+        double s2_, rs_;
+        sqrt_rsqrt_pos(x, s2_, rs_);
+        maxs = std::fmax(maxs, std::fmax(std::fabs(s2_ / std::sqrt(x) - 1), std::fabs(rs_ * std::sqrt(x) - 1)));
         // the controller's use: gamma * e2old^hb2 / e2^hb1 on the range it can reach
         const double e2 = std::exp(std::uniform_real_distribution<double>(-40, 25)(g));
         const double e2o = std::exp(std::uniform_real_distribution<double>(-18.4, 0)(g));
