@@ -729,3 +729,26 @@ def test_random_models_match_oracle(gpu, seed):
     with gpu.Handle(spec) as h:
         for n in (1, 97, 20011):
             compare(h, spec, orc, draw(n, n), int(rng.integers(0, 2)), bool(rng.integers(0, 2)))
+
+
+@pytest.mark.parametrize("nout", [1, 2])
+def test_reference_solve_testset(gpu, nout):
+    """reference test/solve.jl:17-83 ("DiffEq Expectation Solve"): scalar (`sol[1, end]`) and vector-valued
+    (`sol[:, end]`) observables, Koopman with `batch = 20` at `ireltol = iabstol = 1e-3` and MonteCarlo(10000),
+    each against `exp(A t) * mean(u0)` at the reference's `rtol = 1e-2`; the scalar problem returns scalars."""
+    m = gpu.models
+    prob = gpu.ODEProblem(m._LINEAR2_RHS, [1.0, 1.0], (0.0, 3.0), [1.0, 2.0])
+    sm = gpu.SystemMap(prob, gpu.Tsit5(), save_everystep=False)
+    gd = gpu.GenericDistribution(gpu.Uniform(1, 10), gpu.truncated(gpu.Normal(3.0, 1), 0.0, 6.0))
+    g = m.observable_components([0] if nout == 1 else [0, 1])
+    ex = gpu.ExpectationProblem(sm, g, m.hmap_scatter(u0_from_x=[(0, 0), (1, 1)]), gd, nout=nout)
+    analytical = np.array(README["analytical"])[:nout]
+    for quadalg in (gpu.CubatureJLh(), gpu.B200Cubature()):
+        sol = gpu.solve(ex, gpu.Koopman(), quadalg=quadalg, ireltol=1e-3, iabstol=1e-3, batch=20)
+        assert np.allclose(np.atleast_1d(sol.u), analytical, rtol=1e-2)
+        assert np.ndim(sol.u) == (0 if nout == 1 else 1) and np.ndim(sol.resid) == np.ndim(sol.u)
+    mc = gpu.solve(ex, gpu.MonteCarlo(10000))
+    assert np.allclose(np.atleast_1d(mc.u), analytical, rtol=1e-2) and np.ndim(mc.u) == (0 if nout == 1 else 1)
+    with pytest.raises(NotImplementedError):       # the unbatched integrand stays on the reference's CPU path
+        gpu.solve(ex, gpu.Koopman(), quadalg=gpu.CubatureJLh())
+    ex.close()
