@@ -240,7 +240,7 @@ def run_reference(args):
     }
     if not args.no_solves:
         line["expectation_solves"] = time_koopman_solves("cpu")
-    print(json.dumps(line))
+    emit_json_line(line)
     return 0
 
 
@@ -344,27 +344,39 @@ def run_b200(args):
         return float(t.item()), kernel_ms, total_ms, launches, (s, s2, c, st)
 
     def timed_resident(steps, warmup):
-        """The timed region of `value`: K blocking-equivalent steps, each = one launch over the resident samples +
-        (N > 1) its own all-reduce of the 2 nout + 4 results.  The library's split call lets the exchange of step
-        k run on the host and over NVLink while the kernel of step k+1 is already on the GPU; every step still
-        finishes with its own exchange, the last one inside the timed region."""
-        for _ in range(warmup):
-            step_resident()
-        barrier()
+        """The timed region of `value`: K steps, each = one launch over the resident samples + (N > 1) its own
+        all-reduce of the 2 nout + 4 results.  The library's split call keeps the kernel of step k+1 queued behind
+        step k (as a streamed MonteCarlo(10^9) does, block after block), so the device does not wait for the host
+        between steps and the exchange of step k runs on the host and over NVLink while step k+1 computes; every
+        step still finishes with its own exchange, the last one inside the timed region."""
         kernel_ms, total_ms, launches = [], [], 0
-        prev = None
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            h.reduce_samples_begin(xd, npts=n)
-            if prev is not None and world > 1:
-                exchange(*prev)
+        prev, st = None, None
+
+        def retire():
+            nonlocal prev, launches, st
             prev = h.reduce_samples_end()
             st = h.last_stats()
             kernel_ms.append(st["kernel_ms"])
             total_ms.append(st["total_ms"])
             launches += st["launches"]
-        if world > 1:
-            exchange(*prev)
+            if world > 1:
+                exchange(*prev)
+
+        def run_steps(k):
+            h.reduce_samples_begin(xd, npts=n)
+            for _ in range(k - 1):
+                h.reduce_samples_begin(xd, npts=n)   # step j+1 queues behind step j (two pending reductions per handle)
+                retire()                              # result of step j, then its exchange while step j+1 runs
+            retire()
+
+        if warmup > 0:
+            run_steps(warmup)                         # the same pipelined pattern: both reduce slots exist before t0
+        torch.cuda.synchronize()
+        barrier()
+        del kernel_ms[:], total_ms[:]
+        launches = 0
+        t0 = time.perf_counter()
+        run_steps(steps)
         torch.cuda.synchronize()
         t_local = time.perf_counter() - t0
         barrier()
@@ -452,12 +464,35 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
                                     "sample": f"first {ncpu} samples of the same sample set x {reps} passes, {secs:.1f} s, "
                                               "oracle/ (C restatement of the reference path, OpenMP over all host cores)"}
-        print(json.dumps(line))
+        emit_json_line(line)
     xd.free()
     h.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_JSON_FD = None
+
+
+def keep_stdout_for_the_json_line():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on
+    the first collective when the box exports NCCL_DEBUG), so everything else that goes to file descriptor 1 is sent
+    to stderr and the JSON line alone is written to the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json_line(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -478,6 +513,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    keep_stdout_for_the_json_line()
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

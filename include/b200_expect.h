@@ -195,8 +195,10 @@ int b200e_reduce_samples(b200e_handle *h, const double *x, int64_t n, int32_t la
 /* The same reduction split in two for device-resident points on a single-device handle: _begin enqueues the
  * kernel (and the copy of its 2*nout + 4 results) and returns, _end waits and hands the results over.  A caller
  * with an exchange step of its own -- one process per GPU, the all-reduce of the previous batch -- puts that step
- * between the two and overlaps it with the kernel.  One reduction may be pending per handle; x must stay valid
- * and unchanged until _end returns. */
+ * between the two and overlaps it with the kernel.  Up to TWO reductions may be pending per handle (first in, first
+ * out): with the next batch queued behind the running one the device never waits for the host between batches
+ * (a streamed MonteCarlo(10^9), block after block).  Each x must stay valid and unchanged until its _end returns;
+ * no other call on the handle is accepted while a reduction is pending. */
 int b200e_reduce_samples_begin(b200e_handle *h, const double *x, int64_t n, int32_t layout, int32_t weight_by_pdf);
 int b200e_reduce_samples_end(b200e_handle *h, double *sum, double *sumsq, b200e_counters *c);
 

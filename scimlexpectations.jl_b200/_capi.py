@@ -499,7 +499,8 @@ class Handle:
         """Enqueue the reduction of device-resident points and return at once (``reduce_samples_end`` waits)."""
         xp, xk = _as_pointer(x, None)
         self._check(self.L.b200e_reduce_samples_begin(self._h, xp, int(npts), int(layout), int(bool(weight_by_pdf))))
-        self._pending_keep = xk
+        self._pending_keep = getattr(self, "_pending_keep", None) or []
+        self._pending_keep.append(xk)     # up to two in flight, first in first out
 
     def reduce_samples_end(self):
         """Wait for the pending reduction: ``(sum, sumsq, counters)``."""
@@ -507,7 +508,8 @@ class Handle:
         s2 = np.zeros(self.spec.nout)
         c = Counters()
         self._check(self.L.b200e_reduce_samples_end(self._h, s.ctypes.data, s2.ctypes.data, C.byref(c)))
-        self._pending_keep = None
+        if getattr(self, "_pending_keep", None):
+            self._pending_keep.pop(0)
         return s, s2, c.as_dict()
 
     def reduce_generated(self, seed: int, n: int, *, first_index: int = 0):

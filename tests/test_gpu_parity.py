@@ -694,26 +694,47 @@ def test_untruncated_normal_factor(gpu):
 
 def test_split_reduce_call(gpu):
     """b200e_reduce_samples_begin / _end: the device-resident reduction in two halves (a caller's own exchange
-    step goes in between).  Same results as the blocking call; one reduction pending per handle."""
+    step goes in between).  Same results as the blocking call; up to two reductions pending per handle, first in
+    first out, so a streamed MonteCarlo keeps the next batch queued behind the running one."""
     name = "lorenz63"
     n = 200001
     x = sample_points(name, n, seed=61)
+    x2 = sample_points(name, 70001, seed=62)
     with gpu.Handle(gpu.models.builtin(name, schedule=2)) as h:
         d = h.device_array(x.shape).upload(x)
+        d2 = h.device_array(x2.shape).upload(x2)
         ref = h.reduce_samples(d, npts=n)
+        ref2 = h.reduce_samples(d2, npts=len(x2))
         h.reduce_samples_begin(d, npts=n)
         with pytest.raises(gpu.B200Error):
-            h.reduce_samples_begin(d, npts=n)             # one pending reduction per handle
+            h.reduce_samples(d, npts=n)                   # no other call while a reduction is pending
         with pytest.raises(gpu.B200Error):
-            h.reduce_samples(d, npts=n)
-        got = h.reduce_samples_end()
+            h.reduce_generated(1, 1000)
+        h.reduce_samples_begin(d2, npts=len(x2))          # the second batch queues behind the first
+        with pytest.raises(gpu.B200Error):
+            h.reduce_samples_begin(d, npts=n)             # two pending reductions per handle at most
+        got = h.reduce_samples_end()                      # first in ...
+        assert h.last_stats()["kernel_ms"] > 0
+        h.reduce_samples_begin(d, npts=n)                 # ... and its slot is free again
+        got2 = h.reduce_samples_end()
+        got3 = h.reduce_samples_end()
         with pytest.raises(gpu.B200Error):
             h.reduce_samples_end()                        # nothing pending any more
         with pytest.raises(gpu.B200Error):
             h.reduce_samples_begin(x, npts=n)             # host memory: the split form is for resident points
-        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
-        assert h.last_stats()["kernel_ms"] > 0
-        d.free()
+        for g, r in ((got, ref), (got2, ref2), (got3, ref)):
+            assert np.array_equal(g[0], r[0]) and np.array_equal(g[1], r[1]) and g[2] == r[2]
+        # a long stream of batches, two in flight throughout, under the default (dynamic) schedule's rounding
+        with gpu.Handle(gpu.models.builtin(name)) as hs:
+            want = hs.reduce_samples(d, npts=n)
+            hs.reduce_samples_begin(d, npts=n)
+            for _ in range(8):
+                hs.reduce_samples_begin(d, npts=n)
+                s, s2, c = hs.reduce_samples_end()
+                assert c == want[2] and np.allclose(s, want[0], rtol=1e-12) and np.allclose(s2, want[1], rtol=1e-12)
+            hs.reduce_samples_end()
+            assert hs.reduce_samples(d, npts=n)[2] == want[2]
+        d.free(); d2.free()
 
 
 @pytest.mark.parametrize("seed", [0, 5, 8])
