@@ -2,7 +2,9 @@
 #
 # NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  It is a literal mirror of the
 # ctypes calls in scimlexpectations.jl_b200/_capi.py (which ARE tested, on a B200, through the same C
-# ABI), kept short so a maintainer can check it against include/b200_expect.h line by line.
+# ABI), kept short so a maintainer can check it against include/b200_expect.h line by line.  What can be
+# checked without Julia is: tests/test_capi_load.py::test_julia_shim_matches_the_header compares the struct
+# definitions below (field order and machine types) and every ccall's symbol and argument count with the header.
 #
 # What it does: defines `EnsembleB200 <: SciMLBase.EnsembleAlgorithm` for the `ensemblealg` slot of
 # `SystemMap(prob, alg, ensemblealg; kwargs...)` (reference src/system_utils.jl:48-53) and specialises the

@@ -133,3 +133,47 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "expect_oracle" not in text, f
+
+
+def _julia_structs(text):
+    """struct Name ... end blocks of julia/B200Expectations.jl -> {name: [(field, type), ...]} (one-line and
+    multi-line forms, `a::T; b::T` separators, trailing comments)."""
+    out = {}
+    for m in re.finditer(r"^struct\s+(\w+)\s*(?:#[^\n]*)?\n(.*?)^end\b|^struct\s+(\w+);(.*?);\s*end", text, flags=re.S | re.M):
+        name, body = (m.group(1), m.group(2)) if m.group(1) else (m.group(3), m.group(4))
+        body = re.sub(r"#[^\n]*", "", body)
+        out[name] = [(f, t) for f, t in re.findall(r"(\w+)::([\w{}]+)", body)]
+    return out
+
+
+def test_julia_shim_matches_the_header(sme):
+    """julia/B200Expectations.jl cannot run in this image; what can be checked statically is checked: its struct
+    definitions list the same fields, in the same order and with the same machine types, as the ctypes mirror (which
+    `test_field_offsets_match_a_c_compile_of_the_header` ties to the C header), and every `ccall` names an exported
+    entry point with as many arguments as the header declares."""
+    text = open(os.path.join(ROOT, "julia", "B200Expectations.jl")).read()
+    structs = _julia_structs(text)
+    jl2c = {"Int32": C.c_int32, "UInt32": C.c_uint32, "Int64": C.c_int64, "UInt64": C.c_uint64, "Float64": C.c_double}
+    pairs = {"PdfDim": sme._capi.PdfDim, "CModel": sme._capi.Model, "Counters": sme._capi.Counters,
+             "CubatureOpts": sme._capi.CubatureOpts, "CubatureStats": sme._capi.CubatureStats}
+    for jname, ct in pairs.items():
+        assert jname in structs, (jname, sorted(structs))
+        jf = structs[jname]
+        assert [f for f, _ in jf] == [f for f, _ in ct._fields_], jname
+        for (f, jt), (_, cty) in zip(jf, ct._fields_):
+            if jt in jl2c:
+                assert cty is jl2c[jt], (jname, f, jt, cty)
+            elif jt == "Cstring" or jt.startswith("Ptr{"):
+                assert C.sizeof(cty) == C.sizeof(C.c_void_p) and not issubclass(cty, C.Structure), (jname, f)
+            else:
+                assert jt == "Counters" and cty is sme._capi.Counters, (jname, f, jt)
+    # every ccall: exported symbol, argument count = parameter count of the declaration in the header
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "b200_expect.h")).read(), flags=re.S)
+    decl = {m.group(1): m.group(2) for m in re.finditer(r"\b(b200e_\w+)\s*\(([^;{]*?)\)\s*;", header)}
+    calls = re.findall(r"ccall\(\(:(b200e_\w+), LIB\),\s*\w+,\s*\(([^)]*)\)", text)
+    assert len(calls) >= 8
+    for name, argt in calls:
+        assert name in decl, f"{name} is not declared in include/b200_expect.h"
+        n_jl = len([a for a in argt.split(",") if a.strip()])
+        n_c = 0 if decl[name].strip() in ("", "void") else len(decl[name].split(","))
+        assert n_jl == n_c, (name, argt, decl[name])
