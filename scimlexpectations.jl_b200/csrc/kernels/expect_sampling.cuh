@@ -58,7 +58,46 @@ static inline double b200e_s_from_bits(unsigned long long b) { double x; std::me
 #define S_FROM_BITS(b) b200e_s_from_bits(b)
 #endif
 
+// The coefficients of det_log and of AS241 in ONE list.  On the device they are read as constant-bank operands of
+// the FMAs themselves (a 64-bit literal costs two moves every time it is used: 100+ instructions per sample when
+// written inline); the host reads a plain array.  Same values, same operations: the twins stay bit-identical.
+//   [0..9] log series 2/21 .. 2/3;  [10..11] ln2 hi / lo;  [12..27] central region a7..a0, b7..b0 (b0 = 1);
+//   [28..43] intermediate region c7..c0, d7..d0;  [44..59] tail region e7..e0, f7..f0
+#define B200E_SMP_COEFFS                                                                                               \
+    2.0 / 21.0, 2.0 / 19.0, 2.0 / 17.0, 2.0 / 15.0, 2.0 / 13.0, 2.0 / 11.0, 2.0 / 9.0, 2.0 / 7.0, 2.0 / 5.0, 2.0 / 3.0,   \
+    0x1.62e42feep-1, 0x1.a39ef35793c76p-33,                                                                            \
+    2509.0809287301226727, 33430.575583588128105, 67265.770927008700853, 45921.953931549871457,                        \
+    13731.693765509461125, 1971.5909503065514427, 133.14166789178437745, 3.387132872796366608,                         \
+    5226.495278852545925, 28729.085735721942674, 39307.89580009271061, 21213.794301586595867,                          \
+    5394.1960214247511077, 687.1870074920579083, 42.313330701600911252, 1.0,                                           \
+    7.7454501427834140764e-4, 0.0227238449892691845833, 0.24178072517745061177, 1.27045825245236838258,                \
+    3.64784832476320460504, 5.7694972214606914055, 4.6303378461565452959, 1.42343711074968357734,                      \
+    1.05075007164441684324e-9, 5.475938084995344946e-4, 0.0151986665636164571966, 0.14810397642748007459,              \
+    0.68976733498510000455, 1.6763848301838038494, 2.05319162663775882187, 1.0,                                        \
+    2.01033439929228813265e-7, 2.71155556874348757815e-5, 0.0012426609473880784386, 0.026532189526576123093,           \
+    0.29656057182850489123, 1.7848265399172913358, 5.4637849111641143699, 6.6579046435011037772,                       \
+    2.04426310338993978564e-15, 1.4215117583164458887e-7, 1.8463183175100546818e-5, 7.868691311456132591e-4,           \
+    0.0148753612908506148525, 0.13692988092273580531, 0.59983220655588793769, 1.0
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+__constant__ double b200e_smp_coef_dev[60] = {B200E_SMP_COEFFS};  // not const: read from the bank, not folded back into literals
+#endif
+#if !defined(__CUDACC_RTC__)
+static const double b200e_smp_coef_host[60] = {B200E_SMP_COEFFS};
+#endif
+#if defined(__CUDA_ARCH__) || defined(__CUDACC_RTC__)
+#define S_K(i) b200e_smp_coef_dev[i]
+#else
+#define S_K(i) b200e_smp_coef_host[i]
+#endif
+
 namespace b200e_smp {
+// p(r) = ((k[0] r + k[1]) r + ...) r + k[7]: eight coefficients starting at S_K(first)
+B200E_SFN double horner8(int first, double r) {
+    double a = S_K(first);
+#pragma unroll
+    for (int i = 1; i < 8; i++) a = S_FMA(a, r, S_K(first + i));
+    return a;
+}
 
 // ---- Philox4x32-10 ----------------------------------------------------------------------------
 B200E_SFN void philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3, unsigned int k0,
@@ -91,20 +130,13 @@ B200E_SFN double det_log(double x) {
     const double m = S_FROM_BITS(b);
     const double s = S_DIV(S_SUB(m, 1.0), S_ADD(m, 1.0));
     const double z = S_MUL(s, s);
-    double p = 2.0 / 21.0;
-    p = S_FMA(p, z, 2.0 / 19.0);
-    p = S_FMA(p, z, 2.0 / 17.0);
-    p = S_FMA(p, z, 2.0 / 15.0);
-    p = S_FMA(p, z, 2.0 / 13.0);
-    p = S_FMA(p, z, 2.0 / 11.0);
-    p = S_FMA(p, z, 2.0 / 9.0);
-    p = S_FMA(p, z, 2.0 / 7.0);
-    p = S_FMA(p, z, 2.0 / 5.0);
-    p = S_FMA(p, z, 2.0 / 3.0);
+    double p = S_K(0);
+#pragma unroll
+    for (int i = 1; i < 10; i++) p = S_FMA(p, z, S_K(i));
     const double logm = S_FMA(S_MUL(s, z), p, S_MUL(2.0, s));
     const double ed = (double)e;
     // ln 2 = hi + lo with hi on 32 bits: e * hi is exact
-    return S_FMA(ed, 0x1.62e42feep-1, S_FMA(ed, 0x1.a39ef35793c76p-33, logm));
+    return S_FMA(ed, S_K(10), S_FMA(ed, S_K(11), logm));
 }
 
 // ---- Phi^-1(p), 0 < p < 1: Wichura, Algorithm AS241 (Appl. Statist. 37, 1988), routine PPND16 ------
@@ -113,22 +145,7 @@ B200E_SFN double norm_ppf(double p) {
     const double aq = q < 0.0 ? -q : q;
     if (aq <= 0.425) {
         const double r = S_SUB(0.180625, S_MUL(q, q));
-        double a = 2509.0809287301226727;
-        a = S_FMA(a, r, 33430.575583588128105);
-        a = S_FMA(a, r, 67265.770927008700853);
-        a = S_FMA(a, r, 45921.953931549871457);
-        a = S_FMA(a, r, 13731.693765509461125);
-        a = S_FMA(a, r, 1971.5909503065514427);
-        a = S_FMA(a, r, 133.14166789178437745);
-        a = S_FMA(a, r, 3.387132872796366608);
-        double d = 5226.495278852545925;
-        d = S_FMA(d, r, 28729.085735721942674);
-        d = S_FMA(d, r, 39307.89580009271061);
-        d = S_FMA(d, r, 21213.794301586595867);
-        d = S_FMA(d, r, 5394.1960214247511077);
-        d = S_FMA(d, r, 687.1870074920579083);
-        d = S_FMA(d, r, 42.313330701600911252);
-        d = S_FMA(d, r, 1.0);
+        const double a = horner8(12, r), d = horner8(20, r);
         return S_DIV(S_MUL(q, a), d);
     }
     double r = q < 0.0 ? p : S_SUB(1.0, p);
@@ -136,41 +153,11 @@ B200E_SFN double norm_ppf(double p) {
     double val;
     if (r <= 5.0) {
         r = S_SUB(r, 1.6);
-        double a = 7.7454501427834140764e-4;
-        a = S_FMA(a, r, 0.0227238449892691845833);
-        a = S_FMA(a, r, 0.24178072517745061177);
-        a = S_FMA(a, r, 1.27045825245236838258);
-        a = S_FMA(a, r, 3.64784832476320460504);
-        a = S_FMA(a, r, 5.7694972214606914055);
-        a = S_FMA(a, r, 4.6303378461565452959);
-        a = S_FMA(a, r, 1.42343711074968357734);
-        double d = 1.05075007164441684324e-9;
-        d = S_FMA(d, r, 5.475938084995344946e-4);
-        d = S_FMA(d, r, 0.0151986665636164571966);
-        d = S_FMA(d, r, 0.14810397642748007459);
-        d = S_FMA(d, r, 0.68976733498510000455);
-        d = S_FMA(d, r, 1.6763848301838038494);
-        d = S_FMA(d, r, 2.05319162663775882187);
-        d = S_FMA(d, r, 1.0);
+        const double a = horner8(28, r), d = horner8(36, r);
         val = S_DIV(a, d);
     } else {
         r = S_SUB(r, 5.0);
-        double a = 2.01033439929228813265e-7;
-        a = S_FMA(a, r, 2.71155556874348757815e-5);
-        a = S_FMA(a, r, 0.0012426609473880784386);
-        a = S_FMA(a, r, 0.026532189526576123093);
-        a = S_FMA(a, r, 0.29656057182850489123);
-        a = S_FMA(a, r, 1.7848265399172913358);
-        a = S_FMA(a, r, 5.4637849111641143699);
-        a = S_FMA(a, r, 6.6579046435011037772);
-        double d = 2.04426310338993978564e-15;
-        d = S_FMA(d, r, 1.4215117583164458887e-7);
-        d = S_FMA(d, r, 1.8463183175100546818e-5);
-        d = S_FMA(d, r, 7.868691311456132591e-4);
-        d = S_FMA(d, r, 0.0148753612908506148525);
-        d = S_FMA(d, r, 0.13692988092273580531);
-        d = S_FMA(d, r, 0.59983220655588793769);
-        d = S_FMA(d, r, 1.0);
+        const double a = horner8(44, r), d = horner8(52, r);
         val = S_DIV(a, d);
     }
     return q < 0.0 ? -val : val;
