@@ -69,6 +69,29 @@ def test_oracle_lamba_reproduces_the_committed_fixture():
         assert np.allclose(s, GOLD["gbm4_lamba_sum"], rtol=1e-13) and np.allclose(s2, GOLD["gbm4_lamba_sumsq"], rtol=1e-13)
 
 
+def test_host_cubature_twin_in_eight_dimensions(sme):
+    """The Koopman leg of the reference's process-noise test integrates over the 8 KKL coefficients
+    (test/processnoise.jl:19-22).  The restated h-adaptive Genz-Malik driver (cubature.py, the host twin of
+    b200e_koopman_solve) on the closed-form integrand u0 exp(1 + W8(1)) pdf(z): 401 nodes per region, and the
+    expectation within the requested 1e-2 of prod_k M(a_k) (moment generating function of the +-4 sigma
+    truncated normal)."""
+    from scipy.special import ndtr
+    a = np.array([math.sqrt(2.0) * math.sin((k + 0.5) * math.pi) / ((k + 0.5) * math.pi) for k in range(8)])
+    Z = ndtr(4.0) - ndtr(-4.0)
+    u0 = np.array([1.0, 2.0, 3.0, 4.0])
+
+    def f(x):
+        w = np.exp(-0.5 * np.sum(x * x, axis=1)) / ((2 * math.pi) ** 4 * Z ** 8)
+        return (np.exp(1.0 + x @ a) * w)[:, None] * u0[None, :]
+
+    rec = []
+    r = sme.hcubature_v(f, [-4.0] * 8, [4.0] * 8, fdim=4, reltol=1e-2, abstol=1e-2, maxevals=12_000_000, record=rec)
+    exact = u0 * math.e * np.prod(np.exp(a * a / 2) * (ndtr(4 - a) - ndtr(-4 - a)) / Z)
+    assert len(rec[0]) == 401 and all(len(b) % 401 == 0 for b in rec)
+    assert r.converged and np.max(np.abs(r.u - exact) / exact) < 1.1e-2
+    assert np.all(r.resid >= np.abs(r.u - exact) * 0.5)      # the error estimate is not optimistic by more than 2x
+
+
 def test_lamba_model_validation_and_compile(sme, tmp_path):
     spec = sme.models.builtin("gbm4_lamba", cache_dir=str(tmp_path))
     assert spec.solver == sme.models.SOLVER_LAMBA_EM
