@@ -23,16 +23,16 @@ CUDA library and a B200 ``solve`` raises.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
-from typing import Any, Callable, Optional, Sequence
+from dataclasses import dataclass
+from typing import Any, Optional, Sequence
 
 import numpy as np
 from scipy.special import ndtr, ndtri
 
 from . import _capi
-from ._capi import (FP32, FP64, LAYOUT_POINT_MAJOR, ModelSpec, PDF_NONE, PDF_NORMAL, PDF_TABLE, PDF_TRUNCNORMAL,
+from ._capi import (FP32, FP64, LAYOUT_POINT_MAJOR, ModelSpec, PDF_NORMAL, PDF_TABLE, PDF_TRUNCNORMAL,
                     PDF_UNIFORM)
-from .cubature import CubatureResult, hcubature_v
+from .cubature import hcubature_v
 
 # ---------------------------------------------------------------------------------------------
 # distributions (the subset of Distributions.jl the product density table covers)
