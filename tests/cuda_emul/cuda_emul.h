@@ -8,6 +8,7 @@
 // deposit from the reads and a second one the reads from the next deposit.  The kernels only call them in
 // warp-uniform control flow with the full mask, which is what this model requires.
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <barrier>
 #include <cmath>
@@ -88,6 +89,10 @@ inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline T __ldcg(const T *p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __float_as_int(float x) { int b; std::memcpy(&b, &x, 4); return b; }
+inline float __int_as_float(int b) { float x; std::memcpy(&x, &b, 4); return x; }
+using std::max;
+using std::min;
 inline double __longlong_as_double(long long b) { double x; std::memcpy(&x, &b, 8); return x; }
 inline long long __double_as_longlong(double x) { long long b; std::memcpy(&b, &x, 8); return b; }
 

@@ -24,7 +24,7 @@ EMUL = os.path.join(ROOT, "tests", "cuda_emul")
 BLOCK = 64
 
 
-def _build(sme, spec, tmp, *, repro=0, em_spt=2):
+def _build(sme, spec, tmp, *, repro=0, em_spt=2, fp32=0):
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
@@ -33,7 +33,7 @@ def _build(sme, spec, tmp, *, repro=0, em_spt=2):
     exe = os.path.join(tmp, "driver")
     clip = 1 if (spec.dtmax > 0 and spec.dtmax < spec.tspan[1] - spec.tspan[0]) else 0
     defs = dict(B200E_NSTATE=spec.nstate, B200E_NPARAM=spec.nparam, B200E_NX=spec.nx, B200E_NOUT=spec.nout,
-                B200E_NKKL=max(1, spec.n_kkl), B200E_SOLVER=spec.solver, B200E_FP32=0, B200E_BLOCK=BLOCK, B200E_MINBLOCKS=1,
+                B200E_NKKL=max(1, spec.n_kkl), B200E_SOLVER=spec.solver, B200E_FP32=fp32, B200E_BLOCK=BLOCK, B200E_MINBLOCKS=1,
                 B200E_DYNAMIC=1, B200E_REPRO=repro, B200E_NSAVE=len(spec.save_times), B200E_TABLE_PDF=0,
                 B200E_CLIP_DTMAX=clip, B200E_EM_SPT=em_spt)
     cmd = [gxx, "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-I", EMUL, "-I", CSRC, "-I", os.path.join(CSRC, "kernels")]
@@ -195,3 +195,18 @@ def test_generated_models_on_the_cpu(sme, tmp_path, family, seed):
     assert c == co
     bound = 1e-8 * np.sqrt(len(x) * s2o) + 1e-300
     assert np.all(np.abs(s - so) <= bound) and np.all(np.abs(s2 - s2o) <= 1e-8 * s2o + 1e-300)
+
+
+@pytest.mark.parametrize("name", ["linear2", "gbm4_lamba"])
+def test_fp32_mode_kernels_on_the_cpu(sme, tmp_path, name):
+    """fp_mode = B200E_FP32 (docs/src/tutorials/introduction.md:419-433): `real = float` state arithmetic, FP64 sums.
+    Against the FP64 oracle the values agree to single precision and a trajectory takes at most one step more or less."""
+    spec = sme.models.builtin(name, fp_mode=1)
+    tmp = str(tmp_path)
+    exe = _build(sme, spec, tmp, fp32=1)
+    x = sample_points("linear2" if name == "linear2" else "gbm4", 300, seed=5)
+    orc = oracle_for(name) if name != "linear2" else oracle.OracleProblem.builtin(name)
+    ref, cref, sref = orc.eval_nodes(x, weight_by_pdf=True, want_steps=True)
+    dx, steps, _, _, c, _ = _run(exe, spec, tmp, x, "nodes_dyn", grid=2)
+    assert c["nfail"] == 0 and np.abs(steps - sref).max() <= (1 if name == "linear2" else 3)
+    assert np.max(np.abs(dx - ref) / np.abs(ref).max(axis=0)) <= (1e-4 if name == "linear2" else 2e-3)
