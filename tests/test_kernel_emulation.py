@@ -210,3 +210,23 @@ def test_fp32_mode_kernels_on_the_cpu(sme, tmp_path, name):
     dx, steps, _, _, c, _ = _run(exe, spec, tmp, x, "nodes_dyn", grid=2)
     assert c["nfail"] == 0 and np.abs(steps - sref).max() <= (1 if name == "linear2" else 3)
     assert np.max(np.abs(dx - ref) / np.abs(ref).max(axis=0)) <= (1e-4 if name == "linear2" else 2e-3)
+
+
+def test_wide_observable_register_accumulators_on_the_cpu(sme, tmp_path):
+    """64 outputs (32 save times x 2 components): at this block size the per-lane accumulators do not fit the
+    shared-memory columns and fall back to the Accum register arrays; block reduction one column at a time."""
+    times = tuple(np.linspace(0.0, 3.0, 32).tolist())
+    spec = sme.models.builtin("linear2_saveat", save_times=times, nout=64)
+    assert (2 * spec.nout * 8 + 32) * BLOCK > 40960
+    tmp = str(tmp_path)
+    exe = _build(sme, spec, tmp)
+    x = sample_points("linear2_saveat", 150, seed=14)
+    orc = oracle.OracleProblem.from_source(spec.source, nstate=spec.nstate, nparam=spec.nparam, nx=spec.nx, nout=spec.nout,
+                                           u0=spec.u0, p=spec.p, tspan=spec.tspan, pdf=spec.pdf, save_times=spec.save_times)
+    ref, cref, sref = orc.eval_nodes(x, weight_by_pdf=True, want_steps=True)
+    dx, steps, _, _, c, _ = _run(exe, spec, tmp, x, "nodes", grid=2)
+    _check_nodes(dx, steps, c, ref, cref, sref, tol=1e-8)
+    so, s2o, co = orc.reduce_samples(x)
+    for mode in ("reduce", "reduce_dyn"):
+        _, _, s, s2, c, _ = _run(exe, spec, tmp, x, mode, weight=0, grid=2)
+        assert c == co and np.allclose(s, so, rtol=1e-9, atol=1e-12) and np.allclose(s2, s2o, rtol=1e-9)
