@@ -230,3 +230,39 @@ def test_wide_observable_register_accumulators_on_the_cpu(sme, tmp_path):
     for mode in ("reduce", "reduce_dyn"):
         _, _, s, s2, c, _ = _run(exe, spec, tmp, x, mode, weight=0, grid=2)
         assert c == co and np.allclose(s, so, rtol=1e-9, atol=1e-12) and np.allclose(s2, s2o, rtol=1e-9)
+
+
+def test_controller_limits_and_failures_on_the_cpu(sme, tmp_path):
+    """dtmax below the span (the clip is compiled in on demand), maxiters aborts, and NaN / Inf sample points: counted
+    per trajectory exactly as the oracle counts them, every clean column untouched."""
+    name = "lorenz63"
+    x = sample_points(name, 300, seed=15)
+    tmp = str(tmp_path)
+    for kw in (dict(dtmax=0.02), dict(maxiters=9)):
+        spec = sme.models.builtin(name, **kw)
+        exe = _build(sme, spec, tmp)
+        orc = oracle.OracleProblem.builtin(name, **kw)
+        ref, cref, sref = orc.eval_nodes(x, weight_by_pdf=False, want_steps=True)
+        dx, steps, _, _, c, _ = _run(exe, spec, tmp, x, "nodes_dyn", weight=0, grid=2)
+        assert c == cref and np.array_equal(steps, sref), kw
+        assert np.max(np.abs(dx - ref) / np.abs(ref).max(axis=0)) <= 2e-6
+        assert (c["nfail"] == len(x)) == ("maxiters" in kw)
+    spec = sme.models.builtin(name)
+    exe = _build(sme, spec, tmp)
+    orc = oracle.OracleProblem.builtin(name)
+    clean, _, _, _, c_clean, _ = _run(exe, spec, tmp, x, "nodes", weight=0, grid=2)
+    bad = x.copy()
+    bad[7, 3] = np.nan
+    bad[100, 0] = np.inf
+    bad[211, 4] = -np.inf
+    dirty, steps, _, _, c_dirty, _ = _run(exe, spec, tmp, bad, "nodes", weight=0, grid=2)
+    _, cref, sref = orc.eval_nodes(bad, weight_by_pdf=False, want_steps=True)
+    mask = np.ones(len(x), dtype=bool)
+    mask[[7, 100, 211]] = False
+    assert np.array_equal(dirty[mask], clean[mask]) and not np.all(np.isfinite(dirty[~mask]))
+    assert c_clean["nfail"] == 0 and c_dirty["nfail"] == 3 and np.array_equal(steps, sref)
+    assert (c_dirty["naccept"], c_dirty["nreject"]) == (cref["naccept"], cref["nreject"])
+    # known difference on FAILED trajectories only: with an infinite parameter the initial-step heuristic sees
+    # d1 = Inf; the oracle gets dt0 = 0 and takes the "singular" exit (2 evaluations), the kernel's reciprocal of Inf
+    # is NaN, fmin drops it and the regular path runs (3 evaluations): nf differs by one for that trajectory
+    assert 0 <= c_dirty["nf"] - cref["nf"] <= 1
