@@ -1,7 +1,11 @@
 """CPU fuzz of the emulated kernels (tests/cuda_emul) against the oracle on generated models: no GPU needed.
 usage: emul_fuzz.py ode|noise|large <first seed> <end seed>"""
-import os, sys, tempfile, numpy as np, traceback
-sys.path.insert(0,'os.path.dirname(os.path.dirname(os.path.abspath(__file__)))')
+import os
+import sys
+import tempfile
+
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import scimlexpectations_jl_b200 as sme
 from tests.test_kernel_emulation import _build, _run, _check_nodes
 from tests.fuzz_util import oracle_of, random_model, random_noise_model
