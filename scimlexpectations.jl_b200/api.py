@@ -257,7 +257,7 @@ class ProcessNoiseSystemMap:
     def __init__(self, prob: SDEProblem, n: int, *args, **kwargs):
         self.prob = prob
         self.n = int(n)
-        self.args = args      # (EM(dt),) or (LambaEM(),) -- forwarded solve arguments
+        self.args = args      # (EM(dt),) or (LambaEM(),), optionally followed by EnsembleB200(...) -- forwarded solve arguments
         self.kwargs = kwargs  # dt=... / abstol=..., reltol=..., ensemblealg=EnsembleB200(...)
 
 
@@ -297,7 +297,8 @@ class ExpectationProblem:
         S = self.S
         prob = S.prob
         if isinstance(S, ProcessNoiseSystemMap):
-            ens = S.kwargs.get("ensemblealg", EnsembleB200())
+            # the reference forwards args... to solve(ensprob, alg, ensemblealg; ...): the ensemble algorithm is positional there
+            ens = next((a for a in S.args if isinstance(a, EnsembleB200)), S.kwargs.get("ensemblealg", EnsembleB200()))
             alg = next((a for a in S.args if isinstance(a, (EM, LambaEM))), None)
             if alg is None:
                 raise NotImplementedError("the B200 process-noise path implements EM(dt) and LambaEM(); pass one in args")

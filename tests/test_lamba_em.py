@@ -110,6 +110,10 @@ def test_lamba_model_validation_and_compile(sme, tmp_path):
     assert (lowered.solver, lowered.n_kkl, lowered.abstol, lowered.reltol) == (sme.models.SOLVER_LAMBA_EM, 8, 1e-3, 1e-3)
     with pytest.raises(NotImplementedError):
         sme.ExpectationProblem(sme.ProcessNoiseSystemMap(prob, 8), ex.g, ex.h, nout=4).model_spec()
+    # the ensemble algorithm as the second forwarded solve argument, as in solve(ensprob, alg, ensemblealg; ...)
+    sm2 = sme.ProcessNoiseSystemMap(prob, 8, sme.LambaEM(), sme.EnsembleB200(fp32=True, schedule=1), abstol=1e-3, reltol=1e-3)
+    low2 = sme.ExpectationProblem(sm2, ex.g, ex.h, nout=4).model_spec()
+    assert (low2.fp_mode, low2.schedule, low2.solver) == (1, 1, sme.models.SOLVER_LAMBA_EM)
 
 
 # ---------------------------------------------------------------------------------------------------
