@@ -24,9 +24,10 @@
 module B200Expectations
 
 using SciMLExpectations, SciMLBase, Distributions, Statistics
-import SciMLExpectations: build_integrand, ExpectationProblem, SystemMap, Koopman, MonteCarlo,
+import KernelDensity                     # the reference module imports it too (src/SciMLExpectations.jl:4-10) but does not re-export it
+import SciMLExpectations: build_integrand, ExpectationProblem, SystemMap, ProcessNoiseSystemMap, Koopman, MonteCarlo,
                           ExpectationSolution, GenericDistribution
-import Integrals: BatchIntegralFunction
+import Integrals: BatchIntegralFunction, HCubatureJL
 
 const LIB = get(ENV, "B200E_LIB", "libb200expect.so")
 
@@ -61,14 +62,42 @@ Base.@kwdef struct B200Model
     diffusion::String = ""           # process noise only: B200E_FN void diffusion(real* g, const real* u, const real* p, real t)
 end
 
+# One library handle (compiled kernels, streams, device buffers) per (problem, density) of an EnsembleB200.  The
+# finalizer returns it to the library when the cache entry and every integrand closure holding it are gone, so
+# repeated solves neither recompile nor grow device memory.
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    function Handle(ptr::Ptr{Cvoid})
+        h = new(ptr)
+        finalizer(release!, h)
+        return h
+    end
+end
+function release!(h::Handle)
+    if h.ptr != C_NULL
+        ccall((:b200e_destroy, LIB), Cint, (Ptr{Cvoid},), h.ptr)
+        h.ptr = C_NULL
+    end
+    return nothing
+end
+# ccall(..., (Ptr{Cvoid}, ...), h, ...): cconvert keeps the Handle itself rooted for the duration of the call
+Base.cconvert(::Type{Ptr{Cvoid}}, h::Handle) = h
+Base.unsafe_convert(::Type{Ptr{Cvoid}}, h::Handle) = h.ptr
+
 Base.@kwdef struct EnsembleB200 <: SciMLBase.EnsembleAlgorithm
     model::B200Model
+    # factors of the product density, one per dimension of x: Uniform / Normal / truncated(Normal) /
+    # KernelDensity.UnivariateKDE.  `nothing`: taken from GenericDistribution(dists...) (the product constructor,
+    # src/distribution_utils.jl:40-48).  The 4-argument GenericDistribution(pdf_func, rand_func, lb, ub) of the KDE
+    # tutorial (docs/src/tutorials/gpu_bayesian.md:163-166) hides its factors in a user closure: pass them here.
+    dists::Any = nothing
     devices::Vector{Int32} = Int32[]           # empty: current device; several: sharded + one NCCL all-reduce
     fp32::Bool = false
     schedule::Int32 = 0                        # 0 dynamic work distribution, 1 static, 2 dynamic with bit-reproducible sums
     sampler::Symbol = :device                  # MonteCarlo: :device draws rand(d) in the kernel (counter-based
                                                # stream, reproducible by b200e_sample_host); :host ships rand(d)
     seed::UInt64 = 0x0000000000000000
+    cache::Dict{UInt64, Handle} = Dict{UInt64, Handle}()   # handles by problem / density digest (see create_handle)
 end
 
 pdfdim(d::Uniform) = PdfDim(1, 0, minimum(d), maximum(d), 0.0, 1.0, C_NULL, 0)
@@ -76,25 +105,42 @@ pdfdim(d::Normal) = PdfDim(2, 0, -Inf, Inf, mean(d), std(d), C_NULL, 0)
 pdfdim(d::Truncated{<:Normal}) = PdfDim(3, 0, minimum(d), maximum(d), mean(d.untruncated), std(d.untruncated), C_NULL, 0)
 # a KernelDensity.UnivariateKDE (gpu_bayesian.md:153-166); `k.density` must stay alive until b200e_create returns
 pdfdim(k::KernelDensity.UnivariateKDE) = PdfDim(4, 0, first(k.x), last(k.x), 0.0, 1.0, pointer(k.density), length(k.density))
-pdfdim(d) = error("B200Expectations: no device pdf table for $(typeof(d)); supported: Uniform, Normal, truncated(Normal)")
+pdfdim(d) = error("B200Expectations: no device pdf table for $(typeof(d)); supported: Uniform, Normal, truncated(Normal), KernelDensity.UnivariateKDE")
+
+# what identifies a factor in the handle cache (a KDE by its grid ends and a digest of its values, not by identity)
+factor_key(d) = d
+factor_key(k::KernelDensity.UnivariateKDE) = (first(k.x), last(k.x), length(k.density), hash(k.density))
+
+"Factors of the product density of `d` as the library needs them: explicit on the ensemble algorithm, else from the product constructor."
+function density_factors(ens, d)
+    ens.dists === nothing || return ens.dists
+    f = d.pdf_func
+    # GenericDistribution(dists...) builds pdf_func as a closure over `dists` (src/distribution_utils.jl:41-42)
+    hasfield(typeof(f), :dists) && return getfield(f, :dists)
+    error("B200Expectations: this GenericDistribution was built from a user pdf_func; pass its factors as EnsembleB200(dists = (...))")
+end
 
 check(rc, h) = rc == 0 ? nothing :
     error("libb200expect: ", unsafe_string(ccall((:b200e_last_error, LIB), Cstring, (Ptr{Cvoid},), h)), " (status $rc)")
 
-"b200e_create for `exprob` (factors of the product density come from the keyword `dists`)."
-create_handle(exprob::ExpectationProblem, dists) =
-    create_handle(exprob.S.prob, exprob.S.ensemblealg, exprob.S.kwargs, dists)
+"The library handle of `exprob`: created on first use, then served from the ensemble algorithm's cache."
+create_handle(exprob::ExpectationProblem) =
+    create_handle(exprob.S.prob, exprob.S.ensemblealg, exprob.S.kwargs, density_factors(exprob.S.ensemblealg, exprob.d))
 function create_handle(prob, ens::EnsembleB200, kw, dists; solver = 0, n_kkl = 0, dt_fixed = 0.0,
                        default_tol = (1e-6, 1e-3))
     m = ens.model
     u0 = collect(Float64, prob.u0); p = collect(Float64, prob.p === nothing || prob.p isa SciMLBase.NullParameters ? Float64[] : prob.p)
+    key = hash((u0, p, prob.tspan, collect(pairs(kw)), collect(pairs(prob.kwargs)), solver, n_kkl, dt_fixed, default_tol,
+                map(factor_key, Tuple(dists)), m.rhs, m.diffusion, m.hmap, m.observable, m.nout, ens.fp32, ens.schedule, ens.devices))
+    cached = get(ens.cache, key, nothing)
+    cached === nothing || cached.ptr == C_NULL || return cached
     pdf = PdfDim[pdfdim(d) for d in dists]
     src = m.rhs * "\n" * m.diffusion * "\n" * m.hmap * "\n" * m.observable
     # saveat of the ODEProblem (docs/src/tutorials/introduction.md:207-212): the observable is then an
     # `observable_at(k, t, u, p, out)` source and nout = length(saveat) * outputs per save time
     saves = collect(Float64, get(prob.kwargs, :saveat, Float64[]))
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve u0 p pdf src ens saves begin
+    GC.@preserve u0 p pdf src ens saves dists begin
         cm = CModel(sizeof(CModel), length(u0), length(p), length(pdf), m.nout, solver, n_kkl, ens.fp32 ? 1 : 0,
                     Base.unsafe_convert(Cstring, src), pointer(u0), pointer(p),
                     prob.tspan[1], prob.tspan[2], get(kw, :abstol, default_tol[1]), get(kw, :reltol, default_tol[2]),
@@ -105,14 +151,14 @@ function create_handle(prob, ens::EnsembleB200, kw, dists; solver = 0, n_kkl = 0
         rc = ccall((:b200e_create, LIB), Cint, (Ref{CModel}, Ref{Ptr{Cvoid}}), cm, h)
         rc == 0 || error("b200e_create: ", unsafe_string(ccall((:b200e_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
     end
-    return h[]
+    return ens.cache[key] = Handle(h[])
 end
 
 const B200Problem = ExpectationProblem{<:SystemMap{<:Any, <:Any, <:EnsembleB200}}
 
 # ---- Koopman batch integrand (reference src/expectation.jl:169-200) --------------------------------
-function build_integrand(prob::B200Problem, ::Koopman, mid, p, batch::Integer; dists = prob.d.pdf_func.dists)  # the product constructor's closure captures `dists` (distribution_utils.jl:41-42)
-    h = create_handle(prob, dists)
+function build_integrand(prob::B200Problem, ::Koopman, mid, p, batch::Integer)   # the reference's signature: no extra arguments
+    h = create_handle(prob)                       # captured by the closure below: alive as long as the integrand is
     nout = prob.S.ensemblealg.model.nout
     function integrand_koopman_systemmap_batch!(dx, x, _)
         npts = size(x)[end]                       # x :: dim x npts, column-major == point-major layout 0
@@ -136,22 +182,29 @@ struct CubatureStats
     kernel_ms::Float64; total_ms::Float64
     counters::Counters
 end
-function SciMLBase.solve(exprob::B200Problem, ::Koopman, ::B200Cubature; dists = exprob.d.pdf_func.dists,
-                         ireltol = 1e-2, iabstol = 1e-2, maxiters = 1000000, kwargs...)
-    h = create_handle(exprob, dists)
-    nout = exprob.S.ensemblealg.model.nout
+# `quadalg` is a KEYWORD of the reference's solve (src/expectation.jl:336-343): this method intercepts it for B200 problems
+# and hands every other quadrature algorithm to the reference's own method (which calls build_integrand above).
+function SciMLBase.solve(exprob::B200Problem, expalg::Koopman, args...; quadalg = HCubatureJL(), kwargs...)
+    if quadalg isa B200Cubature || any(a -> a isa B200Cubature, args)
+        return koopman_in_library(exprob, create_handle(exprob), exprob.S.ensemblealg.model.nout; kwargs...)
+    end
+    return invoke(SciMLBase.solve, Tuple{ExpectationProblem, Koopman, Vararg{Any}}, exprob, expalg, args...;
+                  quadalg = quadalg, kwargs...)
+end
+function koopman_in_library(exprob, h::Handle, nout; ireltol = 1e-2, iabstol = 1e-2, maxiters = 1000000, batch = nothing, kwargs...)
     lb, ub = collect(Float64, extrema(exprob.d)[1]), collect(Float64, extrema(exprob.d)[2])
     u = zeros(nout); resid = zeros(nout); st = Ref{CubatureStats}()
-    check(ccall((:b200e_koopman_solve, LIB), Cint,
-                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{CubatureOpts}, Ptr{Float64}, Ptr{Float64}, Ref{CubatureStats}),
-                h, lb, ub, CubatureOpts(ireltol, iabstol, maxiters), u, resid, st), h)
-    ccall((:b200e_destroy, LIB), Cint, (Ptr{Cvoid},), h)
+    GC.@preserve h begin
+        check(ccall((:b200e_koopman_solve, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{CubatureOpts}, Ptr{Float64}, Ptr{Float64}, Ref{CubatureStats}),
+                    h, lb, ub, CubatureOpts(ireltol, iabstol, maxiters), u, resid, st), h)
+    end
     return ExpectationSolution(nout == 1 ? u[1] : u, nout == 1 ? resid[1] : resid, st[])
 end
 
 # ---- MonteCarlo (reference src/expectation.jl:268-294) ---------------------------------------------
-function SciMLBase.solve(exprob::B200Problem, expalg::MonteCarlo; dists = exprob.d.pdf_func.dists, block = 1 << 20)
-    h = create_handle(exprob, dists)
+function SciMLBase.solve(exprob::B200Problem, expalg::MonteCarlo; block = 1 << 20)
+    h = create_handle(exprob)
     nout = exprob.S.ensemblealg.model.nout
     total = zeros(nout); s = zeros(nout); s2 = zeros(nout); c = Ref(Counters(0, 0, 0, 0))
     done = 0; n = expalg.trajectories
@@ -174,7 +227,6 @@ function SciMLBase.solve(exprob::B200Problem, expalg::MonteCarlo; dists = exprob
         c[].nfail > 0 && @warn "libb200expect: $(c[].nfail) trajectories aborted (maxiters / non-finite / dt underflow)"
         total .+= s; done += m
     end
-    ccall((:b200e_destroy, LIB), Cint, (Ptr{Cvoid},), h)
     u = total ./ n                                                 # mean(sol.u), expectation.jl:293
     return ExpectationSolution(nout == 1 ? u[1] : u, nothing, nothing)
 end
@@ -183,12 +235,13 @@ end
 # ProcessNoiseSystemMap(prob, n, args...; kwargs...) forwards `args` to solve (src/system_utils.jl:98-100), so the
 # ensemble algorithm is its second positional argument:  ProcessNoiseSystemMap(prob, 8, LambaEM(), EnsembleB200(...);
 # abstol = 1e-3, reltol = 1e-3)  (test/processnoise.jl:15 plus the ensemble slot).  Dispatch is on the type of `args`.
-import SciMLExpectations: ProcessNoiseSystemMap
 const B200NoiseMap = ProcessNoiseSystemMap{<:Any, <:Tuple{Any, EnsembleB200}}
 const B200NoiseProblem = ExpectationProblem{<:B200NoiseMap}
 
-function create_noise_handle(exprob::B200NoiseProblem, dists)
+function create_noise_handle(exprob::B200NoiseProblem)
     S = exprob.S; alg, ens = S.args
+    # the n-fold +-4 sigma truncated normal the reference's constructor builds (src/problem_types.jl:81-85)
+    dists = density_factors(ens, exprob.d)
     name = string(nameof(typeof(alg)))
     if name == "LambaEM"                                   # adaptive: SciML's SDE default tolerances are 1e-2 / 1e-2
         return create_handle(S.prob, ens, S.kwargs, dists; solver = 2, n_kkl = S.n, default_tol = (1e-2, 1e-2))
@@ -198,8 +251,8 @@ function create_noise_handle(exprob::B200NoiseProblem, dists)
     error("B200Expectations: the process-noise path carries EM() and LambaEM(), not $name")
 end
 
-function build_integrand(prob::B200NoiseProblem, ::Koopman, mid, p, batch::Integer; dists = prob.d.pdf_func.dists)
-    h = create_noise_handle(prob, dists)
+function build_integrand(prob::B200NoiseProblem, ::Koopman, mid, p, batch::Integer)
+    h = create_noise_handle(prob)
     nout = prob.S.args[2].model.nout
     function integrand_koopman_processnoisesystemmap_batch!(dx, x, _)
         check(ccall((:b200e_eval_nodes, LIB), Cint,
@@ -212,15 +265,22 @@ function build_integrand(prob::B200NoiseProblem, ::Koopman, mid, p, batch::Integ
     return BatchIntegralFunction{true}(integrand_koopman_processnoisesystemmap_batch!, prototype; max_batch = batch)
 end
 
-function SciMLBase.solve(exprob::B200NoiseProblem, expalg::MonteCarlo; dists = exprob.d.pdf_func.dists)
-    h = create_noise_handle(exprob, dists)
+function SciMLBase.solve(exprob::B200NoiseProblem, expalg::Koopman, args...; quadalg = HCubatureJL(), kwargs...)
+    if quadalg isa B200Cubature || any(a -> a isa B200Cubature, args)
+        return koopman_in_library(exprob, create_noise_handle(exprob), exprob.S.args[2].model.nout; kwargs...)
+    end
+    return invoke(SciMLBase.solve, Tuple{ExpectationProblem, Koopman, Vararg{Any}}, exprob, expalg, args...;
+                  quadalg = quadalg, kwargs...)
+end
+
+function SciMLBase.solve(exprob::B200NoiseProblem, expalg::MonteCarlo)
+    h = create_noise_handle(exprob)
     ens = exprob.S.args[2]; nout = ens.model.nout; n = expalg.trajectories
     s = zeros(nout); s2 = zeros(nout); c = Ref(Counters(0, 0, 0, 0))
     check(ccall((:b200e_reduce_generated, LIB), Cint,     # Z = rand(d) drawn in the kernel (:305), weight 1
                 (Ptr{Cvoid}, UInt64, UInt64, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Counters}),
                 h, ens.seed, 0, n, s, s2, c), h)
     c[].nfail > 0 && @warn "libb200expect: $(c[].nfail) trajectories aborted (maxiters / non-finite / dt underflow)"
-    ccall((:b200e_destroy, LIB), Cint, (Ptr{Cvoid},), h)
     u = s ./ n                                             # mean(sol.u), :324
     return ExpectationSolution(nout == 1 ? u[1] : u, nothing, nothing)
 end
@@ -241,5 +301,5 @@ observable_at_components(idx) =                                 # g(sol,p) = sol
     "B200E_FN void observable_at(int k, real t, const real* u, const real* p, real* out) {\n" *
     join(["  out[$(j-1)] = u[$(i-1)];\n" for (j, i) in enumerate(idx)]) * "}\n"
 
-export EnsembleB200, B200Model, B200Cubature, hmap_scatter, hmap_noise, observable_components, observable_at_components
+export EnsembleB200, B200Model, B200Cubature, release!, hmap_scatter, hmap_noise, observable_components, observable_at_components
 end # module

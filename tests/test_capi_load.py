@@ -177,3 +177,35 @@ def test_julia_shim_matches_the_header(sme):
         n_jl = len([a for a in argt.split(",") if a.strip()])
         n_c = 0 if decl[name].strip() in ("", "void") else len(decl[name].split(","))
         assert n_jl == n_c, (name, argt, decl[name])
+
+
+def test_julia_shim_names_are_imported_and_handles_are_released():
+    """Static checks a Julia parser would make at load time, since the module cannot be loaded here: every
+    qualified `Module.name` the shim uses refers to a module it imports (round 1 shipped `KernelDensity.UnivariateKDE`
+    without importing KernelDensity: an UndefVarError on `using`), no method reaches into `pdf_func.dists` as a
+    default argument, every handle is wrapped in the finalised `Handle` type (no raw b200e_create result is kept),
+    and `quadalg` is taken as the keyword the reference's solve uses (src/expectation.jl:336-343)."""
+    text = open(os.path.join(ROOT, "julia", "B200Expectations.jl")).read()
+    code = "\n".join(line.split("#")[0] if not line.lstrip().startswith('"') else line for line in text.splitlines())
+    code = re.sub(r'"(?:[^"\\]|\\.)*"', '""', code)  # string literals carry C source and messages
+    imported = {"Base", "Core", "GC"}  # always in scope (GC is Base.GC, exported)
+    for m in re.finditer(r"^\s*(?:using|import)\s+([^\n]+)", code, flags=re.M):
+        spec = m.group(1).split(":")[0]
+        imported.update(s.strip() for s in spec.split(",") if s.strip())
+    used = set(re.findall(r"\b([A-Z]\w*)\.[A-Za-z_@]", code))
+    # local bindings that hold structs (field access, not module access)
+    local = {"S", "D", "L", "P"}
+    missing = sorted(u for u in used - imported - local)
+    assert not missing, f"qualified names from modules that are never imported: {missing}"
+    assert "KernelDensity" in imported
+    assert "pdf_func.dists" not in code, "reach for the density factors through density_factors(), not a default argument"
+    # one b200e_create call site, and its result goes straight into a finalised Handle
+    assert len(re.findall(r":b200e_create\b", code)) == 1
+    assert re.search(r"finalizer\(release!, h\)", code) and "Handle(h[])" in code
+    # b200e_destroy is called from release! only
+    assert len(re.findall(r":b200e_destroy\b", code)) == 1
+    # the reference's keyword, on both problem kinds
+    assert len(re.findall(r"solve\(exprob::B200\w*Problem, expalg::Koopman, args\.\.\.; quadalg = HCubatureJL\(\)", code)) == 2
+    # build_integrand keeps the reference's five positional arguments and no keywords (src/expectation.jl:169-172)
+    for m in re.finditer(r"function build_integrand\(([^)]*)\)", code):
+        assert ";" not in m.group(1) and len(m.group(1).split(",")) == 5, m.group(0)
