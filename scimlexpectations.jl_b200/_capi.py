@@ -351,14 +351,28 @@ class DeviceArray:
         self._ptr = None
 
 
-def _as_pointer(x, expect_elems: Optional[int] = None):
-    """(address, keepalive) for a numpy array, PinnedArray, DeviceArray, or anything with data_ptr()."""
+def _as_pointer(x, expect_elems: Optional[int] = None, output: bool = False):
+    """(address, keepalive) for a numpy array, PinnedArray, DeviceArray, or anything with data_ptr().
+
+    An INPUT array of another dtype / stride is passed as a contiguous float64 copy.  An OUTPUT buffer must be
+    written in place, so it has to be float64, C-contiguous and writeable already (a copy would swallow the
+    results): anything else raises."""
     if isinstance(x, PinnedArray):
+        if expect_elems is not None and int(np.prod(x.shape)) != expect_elems:
+            raise ValueError(f"buffer of shape {x.shape} where {expect_elems} elements are expected")
         return x._ptr.value, x
     if isinstance(x, DeviceArray):
+        if expect_elems is not None and int(np.prod(x.shape)) != expect_elems:
+            raise ValueError(f"buffer of shape {x.shape} where {expect_elems} elements are expected")
         return x.ptr, x
     if isinstance(x, np.ndarray):
-        if x.dtype != np.float64 or not x.flags.c_contiguous:
+        if output:
+            if x.dtype != np.float64 or not x.flags.c_contiguous or not x.flags.writeable:
+                raise ValueError("an output buffer must be a writeable C-contiguous float64 array "
+                                 f"(got dtype {x.dtype}, c_contiguous={x.flags.c_contiguous}, writeable={x.flags.writeable})")
+            if expect_elems is not None and x.size != expect_elems:
+                raise ValueError(f"output buffer of shape {x.shape} where {expect_elems} elements are expected")
+        elif x.dtype != np.float64 or not x.flags.c_contiguous:
             x = np.ascontiguousarray(x, dtype=np.float64)
         if expect_elems is not None:
             assert x.size == expect_elems, (x.shape, expect_elems)
@@ -454,7 +468,7 @@ class Handle:
         xp, xk = _as_pointer(x, None)
         if out is None:
             out = np.empty((n, nout) if layout == LAYOUT_POINT_MAJOR else (nout, n), dtype=np.float64)
-        op, ok = _as_pointer(out, None)
+        op, ok = _as_pointer(out, n * nout, output=True)
         steps = None
         if want_steps:
             steps = np.zeros(n, dtype=np.int32)
@@ -532,7 +546,7 @@ class Handle:
         nx = self.spec.nx
         if out is None:
             out = np.empty((n, nx) if layout == LAYOUT_POINT_MAJOR else (nx, n), dtype=np.float64)
-        op, ok = _as_pointer(out, None)
+        op, ok = _as_pointer(out, n * nx, output=True)
         self._check(self.L.b200e_sample_device(self._h, int(seed), int(first_index), int(n), int(layout), op))
         del ok
         return out

@@ -334,7 +334,7 @@ class ExpectationProblem:
 
     def handle(self) -> _capi.Handle:
         spec = self.model_spec()
-        key = repr(spec)
+        key = _spec_key(spec)
         if self._handle is None or self._handle_key != key:
             if self._handle is not None:
                 self._handle.close()
@@ -346,6 +346,24 @@ class ExpectationProblem:
         if self._handle is not None:
             self._handle.close()
             self._handle = None
+
+
+def _spec_key(spec) -> str:
+    """Cache key of a compiled handle: every structured field of the model, with tabulated density factors
+    digested byte for byte (numpy elides the repr of arrays beyond 1000 elements, so two KDE tables with equal
+    ends would otherwise share a handle -- and the stale table in HBM)."""
+    import dataclasses
+    import hashlib
+    d = dataclasses.asdict(spec)
+    pdf = d.pop("pdf")
+    parts = [repr(sorted(d.items()))]
+    for f in pdf or ():
+        f = tuple(f)
+        parts.append(repr(tuple(float(v) for v in f[:5])))
+        if len(f) > 5:
+            tab = np.ascontiguousarray(f[5], dtype=np.float64)
+            parts.append(f"table[{tab.size}]:" + hashlib.sha1(tab.tobytes()).hexdigest())
+    return "|".join(parts)
 
 
 @dataclass
@@ -436,7 +454,12 @@ def build_integrand(prob: ExpectationProblem, alg: Koopman, mid, p, batch: Optio
 def solve(prob: ExpectationProblem, expalg, *, maxiters: int = 1000000, batch: Optional[int] = None,
           quadalg=None, ireltol: float = 1e-2, iabstol: float = 1e-2, record_batches: Optional[list] = None):
     """``solve(exprob, Koopman(); maxiters, batch, quadalg, ireltol, iabstol)`` /
-    ``solve(exprob, MonteCarlo(n))`` (reference src/expectation.jl:336-354, :268-325)."""
+    ``solve(exprob, MonteCarlo(n))`` (reference src/expectation.jl:336-354, :268-325).
+
+    ``batch`` selects the batched integrand (``build_integrand(..., batch::Integer)``) and is stored as
+    ``max_batch`` of the integrand, as in the reference.  It does NOT cap the size of a refinement round under
+    ``CubatureJLh()``: Cubature's ``hcubature_v`` ignores ``max_batch`` (only Cuba's algorithms use it, as
+    ``nvec``), so a round holds as many nodes as the region heap asks for -- here too."""
     if isinstance(expalg, MonteCarlo):
         return _solve_montecarlo(prob, expalg)
     if not isinstance(expalg, Koopman):

@@ -191,3 +191,41 @@ def test_bench_reference_arm_runs_on_the_cpu_box():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert line["config"]["workload"] == "linear2_mc1e7" and line["higher_is_better"] is True
+
+
+def test_output_buffers_are_never_silently_copied():
+    """A strided / float32 / read-only `out` would receive the results in a temporary copy (round-1 advisor finding):
+    output buffers must be writeable C-contiguous float64 of the expected size, inputs may still be converted."""
+    import scimlexpectations_jl_b200 as sme
+    ap = sme._capi._as_pointer
+    big = np.zeros((8, 4))
+    with pytest.raises(ValueError):
+        ap(big[:, 1], 8, output=True)                     # a column view: strided
+    with pytest.raises(ValueError):
+        ap(np.zeros(8, dtype=np.float32), 8, output=True)
+    ro = np.zeros(8)
+    ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        ap(ro, 8, output=True)
+    with pytest.raises(ValueError):
+        ap(np.zeros(7), 8, output=True)                   # wrong element count
+    good = np.zeros((4, 2))
+    addr, keep = ap(good, 8, output=True)
+    assert addr == good.ctypes.data and keep is good      # in place
+    addr, keep = ap(big[:, 1])                            # an input is converted instead
+    assert keep.flags.c_contiguous and keep is not big
+
+
+def test_handle_cache_key_digests_tabulated_factors():
+    """Two KDE tables with equal grid ends and equal head / tail values must not share a compiled handle."""
+    import scimlexpectations_jl_b200 as sme
+    from scimlexpectations_jl_b200.api import _spec_key
+    base = sme.models.builtin("lotka_volterra")
+    n = 2048
+    t1 = np.zeros(n); t2 = np.zeros(n)
+    t1[1000] = 1.0; t2[1001] = 1.0                        # differ only where repr() elides
+    assert repr(t1) == repr(t2)
+    mk = lambda tab: base.replace(pdf=[(sme._capi.PDF_TABLE, 0.0, 1.0, 0.0, 1.0, tab)] + list(base.pdf[1:]))
+    assert _spec_key(mk(t1)) != _spec_key(mk(t2))
+    assert _spec_key(mk(t1)) == _spec_key(mk(t1.copy()))
+    assert _spec_key(base) != _spec_key(base.replace(reltol=1e-4))
