@@ -92,10 +92,12 @@ typedef struct {
     int32_t _pad;
     double lo, hi;    /* support: uniform bounds / truncation bounds (+-inf for plain normal) / table grid ends */
     double mu, sigma; /* normal parameters */
-    /* B200E_PDF_TABLE: density values on the uniform grid lo + i (hi - lo) / (ntable - 1), interpolated
-     * linearly, 0 outside [lo, hi] -- pdf(kde, x) of a KernelDensity estimate
-     * (docs/src/tutorials/gpu_bayesian.md:153-166: pdf_func(x) = prod(pdf.(p_kde, x)), lb / ub = the grid ends).
-     * Koopman only: a tabulated factor cannot be sampled.  The values are copied at b200e_create. */
+    /* B200E_PDF_TABLE: density VALUES on the uniform grid lo + i (hi - lo) / (ntable - 1) -- `k.density` / `k.x` of a
+     * KernelDensity.UnivariateKDE -- evaluated as pdf(kde, x) does: the quadratic B-spline through the values
+     * (Interpolations' BSpline(Quadratic(Line(OnGrid()))): C1, zero second derivative in the end cells), 0 outside
+     * [lo, hi]  (docs/src/tutorials/gpu_bayesian.md:153-166: pdf_func(x) = prod(pdf.(p_kde, x)), lb / ub = the grid
+     * ends).  b200e_create prefilters the values into spline coefficients on the host and copies those; the kernel
+     * evaluates three taps.  Koopman only: a tabulated factor cannot be sampled. */
     const double *table;
     int64_t ntable;
 } b200e_pdf_dim;

@@ -78,6 +78,10 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.orc_logpdf.restype = C.c_double
         L.orc_logpdf.argtypes = [C.POINTER(PdfDim), C.c_int, C.POINTER(C.c_double)]
+        L.orc_pdf.restype = C.c_double
+        L.orc_pdf.argtypes = [C.POINTER(PdfDim), C.c_int, C.POINTER(C.c_double)]
+        L.orc_kde_prefilter.restype = None
+        L.orc_kde_prefilter.argtypes = [C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double)]
         L.orc_kkl_w.restype = C.c_double
         L.orc_kkl_w.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double]
         L.orc_builtin_problem.argtypes = [C.c_char_p, C.POINTER(Problem)]
@@ -94,6 +98,14 @@ def lib():
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def kde_prefilter(values) -> np.ndarray:
+    """Grid values of a KDE -> the n + 2 coefficients of the quadratic B-spline ``pdf(kde, x)`` evaluates."""
+    f = np.ascontiguousarray(values, dtype=np.float64)
+    c = np.empty(len(f) + 2)
+    lib().orc_kde_prefilter(f.ctypes.data_as(C.POINTER(C.c_double)), len(f), c.ctypes.data_as(C.POINTER(C.c_double)))
+    return c
 
 
 class OracleProblem:
@@ -156,10 +168,11 @@ class OracleProblem:
         for a, d in zip(arr, dims):
             kind, lo, hi, mu, sigma = d[:5]
             a.kind, a.lo, a.hi, a.mu, a.sigma = int(kind), float(lo), float(hi), float(mu), float(sigma)
-            if int(kind) == 4:  # tabulated density: (4, lo, hi, 0, 1, values)
-                tab = np.ascontiguousarray(d[5], dtype=np.float64)
+            if int(kind) == 4:  # tabulated density: (4, lo, hi, 0, 1, grid values) -> spline coefficients
+                vals = np.ascontiguousarray(d[5], dtype=np.float64)
+                tab = kde_prefilter(vals)
                 self._keep.append(tab)
-                a.table, a.ntable = tab.ctypes.data_as(C.POINTER(C.c_double)), len(tab)
+                a.table, a.ntable = tab.ctypes.data_as(C.POINTER(C.c_double)), len(vals)
         self._keep.append(arr)
         self.st.pdf = C.cast(arr, C.POINTER(PdfDim))
 
@@ -200,6 +213,11 @@ class OracleProblem:
     def logpdf(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         return float(lib().orc_logpdf(self.st.pdf, self.nx, x.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def pdf(self, x):
+        """pdf(d, x) as the integrand weights with it (tabulated factors multiplied in directly)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        return float(lib().orc_pdf(self.st.pdf, self.nx, x.ctypes.data_as(C.POINTER(C.c_double))))
 
     def eval_nodes(self, x, *, layout=0, weight_by_pdf=True, nthreads=0, want_steps=False):
         """Koopman batch integrand (reference expectation.jl:182-196).

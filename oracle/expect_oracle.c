@@ -69,6 +69,58 @@ int orc_max_threads(void) {
 #endif
 }
 
+/* ---- pdf(kde, x) of a KernelDensity.UnivariateKDE restated (docs/src/tutorials/gpu_bayesian.md:153-166) ----
+ * KernelDensity.jl: pdf(k::UnivariateKDE, x) = pdf(InterpKDE(k), x),
+ *   InterpKDE(k) = extrapolate(scale(interpolate(k.density, BSpline(Quadratic(Line(OnGrid())))), k.x), 0.0).
+ * Interpolations.jl, quadratic B-spline: the data f[1..n] get one padding coefficient on each side, c[0..n+1];
+ * prefiltering_system(Quadratic{Line}) is the (n+2) x (n+2) system
+ *     row 0:        c[0] - 2 c[1] + c[2]            = 0      (zero second derivative in the first cell)
+ *     row i=1..n:   c[i-1]/8 + 3 c[i]/4 + c[i+1]/8  = f[i]   (the spline interpolates the data)
+ *     row n+1:      c[n-1] - 2 c[n] + c[n+1]        = 0
+ * and the value at grid coordinate g (1-based, knot i = round(g), dx = g - i) is
+ *     (dx - 1/2)^2/2 * c[i-1] + (3/4 - dx^2) * c[i] + (dx + 1/2)^2/2 * c[i+1].
+ * Both packages are third-party and not vendored with the reference: restated from package knowledge.
+ * Here the system is solved as written, by banded Gaussian elimination (two sub- and two super-diagonals). */
+void orc_kde_prefilter(const double *f, int64_t n, double *c /* n + 2 */) {
+    const int64_t m = n + 2;
+    /* band storage: A[r][k] = entry (r, r + k - 2), k = 0..4 */
+    double (*A)[5] = calloc((size_t)m, sizeof *A);
+    double *b = calloc((size_t)m, sizeof *b);
+    A[0][2] = 1.0; A[0][3] = -2.0; A[0][4] = 1.0;
+    for (int64_t i = 1; i <= n; i++) { A[i][1] = 0.125; A[i][2] = 0.75; A[i][3] = 0.125; b[i] = f[i - 1]; }
+    A[m - 1][0] = 1.0; A[m - 1][1] = -2.0; A[m - 1][2] = 1.0;
+    for (int64_t r = 0; r < m; r++) {           /* forward elimination, no pivoting (pivots stay >= 0.73) */
+        for (int64_t s = r + 1; s <= r + 2 && s < m; s++) {
+            const int64_t k = 2 - (s - r);      /* column r in row s */
+            const double l = A[s][k] / A[r][2];
+            if (l == 0.0) continue;
+            for (int64_t q = 0; q <= 2; q++)    /* columns r .. r+2 */
+                if (k + q <= 4) A[s][k + q] -= l * A[r][2 + q];
+            b[s] -= l * b[r];
+        }
+    }
+    for (int64_t r = m - 1; r >= 0; r--) {      /* back substitution */
+        double s = b[r];
+        if (r + 1 < m) s -= A[r][3] * c[r + 1];
+        if (r + 2 < m) s -= A[r][4] * c[r + 2];
+        c[r] = s / A[r][2];
+    }
+    free(A);
+    free(b);
+}
+
+/* d->table holds the n + 2 prefiltered coefficients (orc_kde_prefilter), d->ntable = n */
+static double kde_pdf_1d(const orc_pdf_dim *d, double x) {
+    if (!(x >= d->lo && x <= d->hi)) return 0.0;                    /* extrapolate(..., 0) */
+    const int64_t n = d->ntable;
+    const double g = 1.0 + (x - d->lo) * ((double)(n - 1) / (d->hi - d->lo)); /* 1-based grid coordinate */
+    int64_t i = (int64_t)floor(g + 0.5);
+    if (i > n) i = n;
+    const double dx = g - (double)i;
+    const double *c = d->table;                                     /* c[i] is the coefficient of knot i */
+    return 0.5 * (dx - 0.5) * (dx - 0.5) * c[i - 1] + (0.75 - dx * dx) * c[i] + 0.5 * (dx + 0.5) * (dx + 0.5) * c[i + 1];
+}
+
 /* ---- Distributions.logpdf restated (distribution_utils.jl:42 sums these, then one exp) ---- */
 static double std_normal_cdf(double z) { return 0.5 * erfc(-z * M_SQRT1_2); }
 
@@ -82,12 +134,9 @@ static double logpdf_1d(const orc_pdf_dim *d, double x) {
         double z = (x - d->mu) / d->sigma;
         return -0.5 * z * z - log(d->sigma) - half_log_2pi;
     }
-    case ORC_PDF_TABLE: {
+    case ORC_PDF_TABLE: { /* not a log-density: handled by kde_pdf_1d (the spline may dip below 0) */
         if (!(x >= d->lo && x <= d->hi)) return -INFINITY;
-        double g = (x - d->lo) * ((double)(d->ntable - 1) / (d->hi - d->lo));
-        int64_t i = (int64_t)g;
-        if (i > d->ntable - 2) i = d->ntable - 2;
-        double v = d->table[i] + (g - (double)i) * (d->table[i + 1] - d->table[i]);
+        double v = kde_pdf_1d(d, x);
         return v > 0 ? log(v) : -INFINITY;
     }
     case ORC_PDF_TRUNCNORMAL: {
@@ -105,6 +154,17 @@ double orc_logpdf(const orc_pdf_dim *pdf, int nx, const double *x) {
     double s = 0;
     for (int j = 0; j < nx; j++) s += logpdf_1d(&pdf[j], x[j]);
     return s;
+}
+
+/* pdf(d, x): exp(sum of logpdf) over the Distributions factors (distribution_utils.jl:42) times the tabulated
+ * factors multiplied in directly (gpu_bayesian.md:163: pdf_func(x) = prod(pdf.(p_kde, x))) */
+double orc_pdf(const orc_pdf_dim *pdf, int nx, const double *x) {
+    double s = 0, v = 1.0;
+    for (int j = 0; j < nx; j++) {
+        if (pdf[j].kind == ORC_PDF_TABLE) v *= kde_pdf_1d(&pdf[j], x[j]);
+        else s += logpdf_1d(&pdf[j], x[j]);
+    }
+    return exp(s) * v;
 }
 
 /* ---- KKL sine series, expectation.jl:217-220 / :306-309 (absolute t, no rescale) ---- */
@@ -417,7 +477,7 @@ static int solve_point_steps(const orc_problem *pb, const double *x, int weight_
     if (!(pb->solver == ORC_SOLVER_TSIT5 && pb->nsave > 0)) pb->obs(u, p, pb->t1, out);
     if (weight_by_pdf && pb->pdf) {
         /* expectation.jl:180: g(sol, p) * pdf(d, x) */
-        double w = exp(orc_logpdf(pb->pdf, pb->nx, x));
+        double w = orc_pdf(pb->pdf, pb->nx, x);
         for (int k = 0; k < pb->nout; k++) out[k] *= w;
     }
     if (c) { c->nf += nf; c->naccept += nacc; c->nreject += nrej; c->nfail += (uint64_t)failed; }

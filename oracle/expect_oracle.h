@@ -54,8 +54,9 @@ typedef struct {
     int32_t _pad;
     double lo, hi;    /* support (uniform bounds / truncation bounds); +-inf for normal */
     double mu, sigma; /* normal parameters (unused for uniform) */
-    /* ORC_PDF_TABLE: pdf(kde, x) of a KernelDensity estimate (docs/src/tutorials/gpu_bayesian.md:153-166):
-     * ntable values on the uniform grid lo .. hi, linear interpolation, 0 outside */
+    /* ORC_PDF_TABLE: pdf(kde, x) of a KernelDensity estimate (docs/src/tutorials/gpu_bayesian.md:153-166) on the
+     * uniform grid lo .. hi of ntable points: quadratic B-spline (Interpolations' Quadratic(Line(OnGrid()))), 0
+     * outside.  `table` holds the ntable + 2 prefiltered coefficients orc_kde_prefilter makes of the grid values */
     const double *table;
     int64_t ntable;
 } orc_pdf_dim;
@@ -97,6 +98,10 @@ typedef struct {
 
 /* log pdf of the product distribution at x (sum of per-dim logpdf); -inf outside support */
 double orc_logpdf(const orc_pdf_dim *pdf, int nx, const double *x);
+/* pdf of the product distribution at x: exp(sum of logpdf) times the tabulated (KDE) factors */
+double orc_pdf(const orc_pdf_dim *pdf, int nx, const double *x);
+/* grid values f[n] of a KDE -> the n + 2 quadratic B-spline coefficients pdf(kde, x) evaluates */
+void orc_kde_prefilter(const double *f, int64_t n, double *c);
 
 /* one trajectory: x -> h -> solve -> g (-> * pdf).  Returns 0 ok, 1 if the trajectory failed
  * (g is still applied to the last state, as the reference does with failed retcodes). */

@@ -98,8 +98,8 @@ class Truncated:
 class UnivariateKDE:
     """A density tabulated on a uniform grid -- what ``kde(samples)`` of KernelDensity.jl returns (fields ``x``,
     ``density``) and what ``pdf(kde, x)`` interpolates (docs/src/tutorials/gpu_bayesian.md:153-166:
-    ``pdf_func(x) = prod(pdf.(p_kde, x))``, ``lb / ub`` = the grid ends).  Linear interpolation between grid
-    points, 0 outside.  Koopman only (``rand_func() = nothing`` in the tutorial): it cannot be sampled."""
+    ``pdf_func(x) = prod(pdf.(p_kde, x))``, ``lb / ub`` = the grid ends).  Quadratic B-spline through the grid
+    values (KernelDensity's ``InterpKDE`` default), 0 outside.  Koopman only (``rand_func() = nothing`` in the tutorial): it cannot be sampled."""
 
     def __init__(self, x, density):
         self.x = np.ascontiguousarray(x, dtype=np.float64)
@@ -127,8 +127,36 @@ class UnivariateKDE:
     def minimum(self): return float(self.x[0])
     def maximum(self): return float(self.x[-1])
 
+    def spline_coefficients(self) -> np.ndarray:
+        """The ``n + 2`` coefficients of the quadratic B-spline through the grid values with zero second derivative
+        in the end cells -- Interpolations' ``BSpline(Quadratic(Line(OnGrid())))``, what KernelDensity's
+        ``pdf(kde, x)`` evaluates (the library does the same prefilter in ``b200e_create``)."""
+        if getattr(self, "_coef", None) is None:
+            from scipy.linalg import solve_banded
+            f, n = self.density, len(self.density)
+            c = np.empty(n + 2)
+            c[1], c[n] = f[0], f[-1]
+            if n > 2:
+                ab = np.zeros((3, n - 2))
+                ab[0, 1:], ab[1, :], ab[2, :-1] = 0.125, 0.75, 0.125
+                rhs = f[1:-1].copy()
+                rhs[0] -= 0.125 * c[1]
+                rhs[-1] -= 0.125 * c[n]
+                c[2:n] = solve_banded((1, 1), ab, rhs)
+            c[0], c[n + 1] = 2 * c[1] - c[2], 2 * c[n] - c[n - 1]
+            self._coef = c
+        return self._coef
+
     def pdf(self, x):
-        return float(np.interp(x, self.x, self.density, left=0.0, right=0.0))
+        """``pdf(kde, x)``: quadratic B-spline interpolation of the grid values, 0 outside the grid."""
+        x = float(x)
+        if not (self.x[0] <= x <= self.x[-1]):
+            return 0.0
+        n, c = len(self.x), self.spline_coefficients()
+        g = (x - self.x[0]) * (n - 1) / (self.x[-1] - self.x[0])
+        i = min(int(g + 0.5), n - 1)
+        d = g - i
+        return float(0.5 * (d - 0.5) ** 2 * c[i] + (0.75 - d * d) * c[i + 1] + 0.5 * (d + 0.5) ** 2 * c[i + 2])
 
     def logpdf(self, x):
         v = self.pdf(x)

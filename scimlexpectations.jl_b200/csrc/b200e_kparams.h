@@ -17,7 +17,7 @@
 struct b200e_kpdf {
     double lo, hi, mu, inv_sigma, logc;
     double smp_a, smp_b, smp_c, smp_d;
-    const double *tab;   // kind 4: density table on the uniform grid lo + i / inv_dx (device memory), ntab entries
+    const double *tab;   // kind 4: ntab + 2 quadratic B-spline coefficients of the density on the uniform grid lo + i / inv_dx (device memory; knot i <-> tab[i + 1])
     double inv_dx;
     int kind;
     int ntab;

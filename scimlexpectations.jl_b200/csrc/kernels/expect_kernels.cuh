@@ -44,14 +44,19 @@ __device__ __forceinline__ double pdf_weight(const b200e_kparams &P, const doubl
             const double xj = xs[j];
             const bool inside = (xj >= P.pdf[j].lo) && (xj <= P.pdf[j].hi);
             if (B200E_TABLE_PDF && kind == 4) {  // compiled in only when the model has a tabulated factor
-                // tabulated factor (a KDE): linear interpolation on the uniform grid, 0 outside
+                // tabulated factor (a KDE): pdf(kde, x) of KernelDensity = the quadratic B-spline through the grid
+                // values (Interpolations' BSpline(Quadratic(Line(OnGrid()))), 0 outside).  The host prefiltered the
+                // values into ntab + 2 coefficients (knot i <-> tab[i + 1]); three taps around the nearest knot:
+                //   d = g - i in [-1/2, 1/2]:  (d - 1/2)^2 / 2 * c[i-1] + (3/4 - d^2) * c[i] + (d + 1/2)^2 / 2 * c[i+1]
                 double v = 0.0;
                 if (inside) {
                     const double g = (xj - P.pdf[j].lo) * P.pdf[j].inv_dx;
-                    int i = (int)g;
-                    i = i < P.pdf[j].ntab - 2 ? i : P.pdf[j].ntab - 2;
-                    const double a = __ldg(P.pdf[j].tab + i), b = __ldg(P.pdf[j].tab + i + 1);
-                    v = fma(g - (double)i, b - a, a);
+                    int i = (int)(g + 0.5);
+                    i = i < P.pdf[j].ntab - 1 ? i : P.pdf[j].ntab - 1;
+                    const double d = g - (double)i, dm = d - 0.5, dp = d + 0.5;
+                    const double *c = P.pdf[j].tab + i;
+                    const double cm = __ldg(c), c0 = __ldg(c + 1), cp = __ldg(c + 2);
+                    v = fma(0.5 * dm * dm, cm, fma(0.75 - d * d, c0, 0.5 * dp * dp * cp));
                 }
                 tabulated *= v;
             } else {
@@ -301,6 +306,10 @@ __device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long lo
     // d0 = sqrt(s0/N), d1 = sqrt(s1/N):  d0 < 1e-5  <=>  s0 < N * 1e-10
     const real tiny2 = R_(1e-10) * R_(N);
     real dt0 = (s0 < tiny2 || s1 < tiny2) ? R_(1e-6) : R_(0.01) * sqrt_pos(s0 * rcp_pos(s1));
+    // d1 = Inf over a finite d0 (an infinite parameter or state derivative): the reference's d0 / d1 is exactly 0
+    // and the solve takes ode_determine_initdt's "singular" exit below after two evaluations; the reciprocal
+    // above would turn Inf into NaN, which fmin drops (the regular path, one evaluation more)
+    if (s1 == (real)__longlong_as_double(0x7ff0000000000000LL) && s0 < s1) dt0 = R_(0.0);
     dt0 = fmin(dt0, dtmax);
 #if B200E_FP32
     const real eps10 = R_(10.0) * R_(1.1920928955078125e-07);

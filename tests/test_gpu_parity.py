@@ -534,7 +534,7 @@ def test_non_finite_inputs_are_contained(gpu):
         bad[7, 3] = np.nan       # u0[0] = NaN
         bad[100, 0] = np.inf     # sigma = Inf
         bad[2049, 4] = -np.inf   # u0[1] = -Inf
-        dirty = h.eval_nodes(bad, weight_by_pdf=False)
+        dirty, steps = h.eval_nodes(bad, weight_by_pdf=False, want_steps=True)
         c_dirty = h.last_counters()
         s, s2, c_red = h.reduce_samples(bad)
     rows = np.array([7, 100, 2049])
@@ -543,8 +543,13 @@ def test_non_finite_inputs_are_contained(gpu):
     assert np.array_equal(dirty[mask], clean[mask])
     assert not np.all(np.isfinite(dirty[rows]))
     assert c_dirty["nfail"] == 3 and c_clean["nfail"] == 0 and c_red["nfail"] == 3
+    # every counter of the dirty batch -- RHS evaluations of the three FAILED trajectories included (an infinite
+    # parameter: d1 = Inf, the reference's "singular" initial-step exit after two evaluations) -- equals the oracle's
     orc = oracle.OracleProblem.builtin(name)
-    assert orc.eval_nodes(bad, weight_by_pdf=False)[1]["nfail"] == 3
+    _, cref, sref = orc.eval_nodes(bad, weight_by_pdf=False, want_steps=True)
+    assert cref["nfail"] == 3
+    assert c_dirty == cref and c_red == cref, (c_dirty, c_red, cref)
+    assert np.array_equal(steps, sref)
 
 
 def test_centralmoment_reference_testset(gpu):
