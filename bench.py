@@ -7,7 +7,13 @@ A "step" is one pass of the hot path over one batch of synthetic input:
 Default workload = BASELINE.json configs[1]: the README 2-state linear ODE, MonteCarlo(10^7) on a
 shared host-generated sample set (seeded, block-keyed; tests/sampling_util.py).  Each rank owns its
 own 10^7-sample blocks of the stream ("scaling": "weak", no data-path collective besides the final
-all-reduce of O(10) numbers).
+all-reduce of O(10) numbers).  Next to `value` every line carries
+  * "strong": whole-solve wall times at a FIXED total (BASELINE configs[3] lorenz63 MonteCarlo(10^9), and configs[1]
+    at its quoted 10^7 where the latency floor shows) split over the N ranks -- north_star's strong-scaling claim;
+  * "in_library" (N > 1): the same legs through ONE process that owns all N GPUs (n_devices = N in b200e_model:
+    ncclCommInitAll + one grouped ncclAllReduce inside the library) -- what a single-process caller such as the
+    Julia shim gets;
+  * "e2e_pageable": e2e from an ordinary (pageable) host array, what Integrals / Cubature hand f!(dx, x, p).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
@@ -202,6 +208,36 @@ def time_koopman_solves(arm: str, reps: int = 3):
     return out
 
 
+def core_config(args, model, n_full, desc, nx):
+    """The keys that name the workload: identical in both arms (the driver compares them)."""
+    return {"workload": args.workload, "model": model, "description": desc,
+            "samples_per_gpu_per_step": int(n_full),
+            "sample_set": f"PCG64(SeedSequence([{args.seed}, block])), blocks of 2^20",
+            "l2": f"input {n_full * nx * 8 / 1e6:.0f} MB per GPU > 126 MB L2" if n_full * nx * 8 > 126e6 else "input smaller than L2"}
+
+
+def gpu_numa_cpus(index: int):
+    """CPUs of the NUMA node the GPU hangs off (None when the box has one node or sysfs does not say)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        return node, (cpus or None)
+    except Exception:
+        return None, None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -218,7 +254,7 @@ def run_reference(args):
     rate = len(x_cal) / (time.perf_counter() - t0)
     n = int(min(n_full, max(1 << 17, rate * 2.0)))
     x = np.empty((n, orc.nx))
-    make_samples(model, n, 7, 0, x)
+    make_samples(model, n, args.seed, 0, x)
     for _ in range(args.warmup):
         orc.reduce_samples(x, nthreads=cores)
     t0 = time.perf_counter()
@@ -230,11 +266,11 @@ def run_reference(args):
         "impl": "reference", "metric": "ODE-solve integrand evals/sec", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "model": model, "description": desc,
-                   "samples_per_step": n, "note": "bounded sample of the workload; CPU restatement of the reference's "
-                   "EnsembleThreads path (Julia is not installed in this image, the reference cannot run)"},
+        "config": core_config(args, model, n_full, desc, orc.nx),
+        "reference_note": "CPU restatement of the reference's EnsembleThreads path (Julia is not installed in this "
+                          "image, the reference cannot run); each step is a bounded sample of the workload",
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} samples of {args.workload} per step, OpenMP over {cores} threads"},
+                         "sample": f"first {n} samples of the workload's sample set per step, OpenMP over {cores} threads"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -242,6 +278,125 @@ def run_reference(args):
         line["expectation_solves"] = time_koopman_solves("cpu")
     emit_json_line(line)
     return 0
+
+
+STRONG_CASES = (
+    # name, model, FIXED total samples of the whole solve, warm-up samples per rank
+    ("lorenz63_mc1e9", "lorenz63", 10**9),      # BASELINE configs[3]
+    ("linear2_mc1e7", "linear2", 10**7),        # BASELINE configs[1] at its quoted size: the latency floor
+)
+
+
+def strong_scaling_legs(sme, args, world, rank, local_rank, barrier):
+    """north_star: '>85 % strong-scaling efficiency from 1 to 8 GPUs'.  The TOTAL sample count of a solve is fixed;
+    rank r of R draws and solves indices [r n/R, (r+1) n/R) of the counter-based stream inside its kernel
+    (b200e_reduce_generated), one all-reduce of the 2 nout + 4 numbers finishes the solve.  Wall time of the whole
+    solve: barrier + synchronize on both sides, max over ranks, best of `reps`.  The expectation and the integer
+    RHS-evaluation count must not depend on R (sample <-> index mapping is independent of the sharding)."""
+    import torch
+    import torch.distributed as dist
+    if args.no_strong:
+        return None
+    out = {}
+    for name, model, total in STRONG_CASES:
+        lo, hi = total * rank // world, total * (rank + 1) // world
+        with sme.Handle(sme.models.builtin(model, devices=[local_rank])) as hs:
+            nout = hs.spec.nout
+            red = torch.zeros(2 * nout + 4, dtype=torch.float64, device="cuda")
+            stage = torch.zeros(2 * nout + 4, dtype=torch.float64).pin_memory()
+
+            def solve():
+                s, s2, c = hs.reduce_generated(args.seed, hi - lo, first_index=lo)
+                a = stage.numpy()
+                a[:nout], a[nout:2 * nout] = s, s2
+                a[2 * nout:] = (c["nf"], c["naccept"], c["nreject"], c["nfail"])
+                red.copy_(stage, non_blocking=True)
+                if world > 1:
+                    dist.all_reduce(red)
+                return red.cpu().numpy()
+
+            hs.reduce_generated(1, min(hi - lo, 10**6))   # module load, buffers
+            solve()
+            reps = 3 if total >= 10**8 else 20
+            times = []
+            for _ in range(reps):
+                barrier()
+                t0 = time.perf_counter()
+                r = solve()
+                torch.cuda.synchronize()
+                dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                times.append(float(dt.item()))
+            kms = hs.last_stats()["kernel_ms"]
+        best = min(times)
+        out[name] = {"total_samples": total, "n_gpus": world, "wall_s": best, "median_wall_s": float(np.median(times)),
+                     "evals_per_s": total / best, "kernel_ms_rank0": kms, "reps": reps,
+                     "expectation": (r[:nout] / total).tolist(), "nf": int(r[2 * nout]), "nfail": int(r[2 * nout + 3]),
+                     "api": "b200e_reduce_generated per rank + one all-reduce (torch.distributed, NCCL)"}
+    return out
+
+
+def in_library_legs(sme, args, world, rank, model, n, nx, x_rank0):
+    """The drop-in mode of a single-process caller (the reference consumes ONE ensemblealg in ONE process,
+    src/expectation.jl:191, :290): one handle with n_devices = N; the library shards the samples in contiguous index
+    ranges over its devices and finishes with ncclCommInitAll's communicator -- one grouped ncclAllReduce of the
+    2 nout + 4 numbers (b200_expect.cu exchange_results).  Rank 0 drives all N GPUs while the other ranks wait on a
+    CPU (gloo) barrier with their GPUs idle."""
+    import torch
+    import torch.distributed as dist
+    if world == 1 or args.no_inlib:
+        return None
+    cpu_group = dist.new_group(backend="gloo")
+    res = None
+    torch.cuda.synchronize()
+    dist.barrier(group=cpu_group)
+    if rank == 0:
+        res = {"n_devices": world, "process": "one (rank 0), ncclCommInitAll + grouped ncclAllReduce inside libb200expect"}
+        devs = list(range(world))
+
+        def timeit(fn, steps, warmup=3):
+            for _ in range(warmup):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                out = fn()
+            return (time.perf_counter() - t0) / steps, out
+
+        with sme.Handle(sme.models.builtin(model, devices=devs)) as hm:
+            nout = hm.spec.nout
+            # (1) the public MonteCarlo call, rand(d) in the kernel: N x n samples per call (weak, like e2e_device_sampling)
+            dt, (s, s2, c) = timeit(lambda: hm.reduce_generated(args.seed, world * n), args.steps)
+            res["e2e_device_sampling"] = {"value": world * n / dt, "unit": "evals/s", "ms_per_step": dt * 1e3,
+                                          "expectation": (s / (world * n)).tolist(), "nf": c["nf"]}
+            # (2) host-fed: one pinned buffer of N x n samples, sharded by the library over its devices
+            xall = hm.pinned((world * n, nx))
+            for r in range(world):
+                nb = (n + BLOCK - 1) // BLOCK
+                make_samples(model, n, args.seed, r * nb, xall.array[r * n:(r + 1) * n])
+            e_steps = max(3, args.steps // 4)
+            dt, (s, s2, c) = timeit(lambda: hm.reduce_samples(xall), e_steps)
+            st = hm.last_stats()
+            res["e2e"] = {"value": world * n / dt, "unit": "evals/s", "ms_per_step": dt * 1e3,
+                          "h2d_bytes_per_step": int(st["h2d_bytes"]), "expectation": (s / (world * n)).tolist(),
+                          "nf": c["nf"], "api": "b200e_reduce_samples(host pinned x, n_devices = N) -> host sums"}
+            xall.free()
+        if not args.no_strong:
+            res["strong"] = {}
+            for name, smodel, total in STRONG_CASES:
+                with sme.Handle(sme.models.builtin(smodel, devices=devs)) as hs:
+                    hs.reduce_generated(1, world * 10**6)
+                    reps = 3 if total >= 10**8 else 20
+                    times = []
+                    for _ in range(reps):
+                        t0 = time.perf_counter()
+                        s, s2, c = hs.reduce_generated(args.seed, total)
+                        times.append(time.perf_counter() - t0)
+                    res["strong"][name] = {"total_samples": total, "wall_s": min(times), "median_wall_s": float(np.median(times)),
+                                           "evals_per_s": total / min(times), "expectation": (s / total).tolist(),
+                                           "nf": c["nf"], "nfail": c["nfail"]}
+    dist.barrier(group=cpu_group)
+    return res
 
 
 def run_b200(args):
@@ -270,8 +425,16 @@ def run_b200(args):
 
     # rank r owns blocks [r*nb, (r+1)*nb) of the seeded stream: same sets the CPU oracle sees in tests
     nb = (n + BLOCK - 1) // BLOCK
+    # host-fed legs: the rank's pinned buffer is allocated and first touched on the NUMA node of its GPU
+    numa_node, numa_cpus = gpu_numa_cpus(local_rank)
+    old_aff = os.sched_getaffinity(0)
+    if numa_cpus:
+        os.sched_setaffinity(0, numa_cpus)
     xp = h.pinned((n, nx))
     make_samples(model, n, args.seed, rank * nb, xp.array)
+    xpage = np.array(xp.array, copy=True)   # an ordinary (pageable) array: what f!(dx, x, p) receives from Cubature
+    if numa_cpus:
+        os.sched_setaffinity(0, old_aff)
     xd = h.device_array((n, nx)).upload(xp.array)
 
     # the path's one exchange step: all-reduce of the 2*nout sums + 4 counters (counters < 2^53 as doubles)
@@ -302,6 +465,14 @@ def run_b200(args):
 
     def step_e2e():
         s, s2, c = h.reduce_samples(xp)  # pinned host buffer: H2D inside the call, sums come back D2H
+        st = h.last_stats()
+        if world > 1:
+            exchange(s, s2, c)
+            torch.cuda.synchronize()
+        return s, s2, c, st
+
+    def step_pageable():
+        s, s2, c = h.reduce_samples(xpage)  # pageable host memory: the library stages it (host-fed path)
         st = h.last_stats()
         if world > 1:
             exchange(s, s2, c)
@@ -389,9 +560,12 @@ def run_b200(args):
     sampler.start()
     T, kernel_ms, total_ms, launches, (s, s2, c, st) = timed_resident(args.steps, args.warmup)
     clocks = sampler.stop()
-    Te, _, e_total_ms, _, (se, s2e, ce, ste) = timed(step_e2e, max(3, args.steps // 4), 3)
     e_steps = max(3, args.steps // 4)
+    Te, _, e_total_ms, _, (se, s2e, ce, ste) = timed(step_e2e, e_steps, 3)
+    Tp, _, _, _, (sp_, _, cp_, stp) = timed(step_pageable, e_steps, 3)
     Tg, g_kernel_ms, _, _, (sg, s2g, cg, stg) = timed(step_generated, args.steps, 3)
+    strong = strong_scaling_legs(sme, args, world, rank, local_rank, barrier)
+    in_library = in_library_legs(sme, args, world, rank, model, n, nx, xp.array if world > 1 else None)
 
     # per-rank device times and clocks (outside the timed regions): the job moves at the pace of its slowest GPU
     per_rank = None
@@ -423,17 +597,23 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": T / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "model": model, "description": desc,
-                       "samples_per_gpu_per_step": n, "sample_set": f"PCG64(SeedSequence([{args.seed}, block])), blocks of 2^20",
-                       "l2": f"input {n * nx * 8 / 1e6:.0f} MB per GPU > 126 MB L2" if n * nx * 8 > 126e6 else "input smaller than L2",
-                       "grid": st["grid"], "block": st["block"], "regs": st["regs_per_thread"],
-                       "refill_threshold": args.refill or "auto", "parallelism": f"samples sharded over {world} GPU(s)"},
+            "config": core_config(args, model, n, desc, nx),
+            "launch": {"grid": st["grid"], "block": st["block"], "regs": st["regs_per_thread"],
+                       "local_bytes_per_thread": st["local_bytes_per_thread"],
+                       "refill_threshold": args.refill or "auto", "parallelism": f"samples sharded over {world} GPU(s)",
+                       "pinned_buffer_numa_node": numa_node},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(ste["h2d_bytes"]),
                     "d2h_bytes_per_step": int(ste["d2h_bytes"]), "ms_per_step": Te / e_steps * 1e3,
                     "api": "b200e_reduce_samples(host pinned x) -> host sums"},
             # not the contract's e2e (its inputs never exist on the host): the public MonteCarlo call with the
             # sampler inside the kernel, the configuration a user of solve(exprob, MonteCarlo(n)) runs
+            # the same call from pageable host memory (a numpy array; Julia's Array handed to f!(dx, x, p))
+            "e2e_pageable": {"value": world * n * e_steps / Tp, "unit": "evals/s", "h2d_bytes_per_step": int(stp["h2d_bytes"]),
+                             "d2h_bytes_per_step": int(stp["d2h_bytes"]), "ms_per_step": Tp / e_steps * 1e3,
+                             "slowdown_vs_pinned": Tp / Te,
+                             "api": "b200e_reduce_samples(host pageable x) -> host sums"},
+            "strong": strong,
             "e2e_device_sampling": {"value": world * n * args.steps / Tg, "unit": "evals/s", "h2d_bytes_per_step": 0,
                                     "d2h_bytes_per_step": int(stg["d2h_bytes"]), "ms_per_step": Tg / args.steps * 1e3,
                                     "kernel_ms": float(np.mean(g_kernel_ms)),
@@ -443,7 +623,10 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64" if not args.fp32 else "fp32", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "kernel": "b200e_reduce", "kernel_ms": k_ms,
+                         # the instantiation the library launches for this batch (dynamic work distribution
+                         # whenever the batch holds more than one point per lane, b200_expect.cu use_dynamic)
+                         "kernel": "b200e_reduce_dyn" if n > st["grid"] * st["block"] else "b200e_reduce",
+                         "kernel_ms": k_ms,
                          "flops_per_launch": flops,
                          "peak_source": "b200e_measure_fma_peak (FMA-chain microbenchmark run in this process; "
                                         "MEASURED_PEAKS.json has no FP64 entry)",
@@ -453,6 +636,8 @@ def run_b200(args):
         }
         if per_rank is not None:
             line["per_rank"] = per_rank
+        if in_library is not None:
+            line["in_library"] = in_library
         if world == 1 and not args.no_solves:
             line["expectation_solves"] = time_koopman_solves("b200")
         if world == 1 and not args.no_cpu:
@@ -510,6 +695,8 @@ def main():
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-solves", action="store_true", help="skip the Koopman whole-solve timings")
+    ap.add_argument("--no-strong", action="store_true", help="skip the fixed-total (strong scaling) whole-solve legs")
+    ap.add_argument("--no-inlib", action="store_true", help="skip the single-process n_devices = N legs (N > 1)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

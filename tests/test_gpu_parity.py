@@ -16,6 +16,7 @@ import numpy as np
 import pytest
 
 import oracle
+from tests.conftest import record_parity
 from tests.sampling_util import sample_points
 
 pytestmark = pytest.mark.gpu
@@ -68,6 +69,7 @@ def test_nodes_mode_matches_oracle(gpu, name):
     assert c == cref                      # nf / naccept / nreject / nfail bit-exact
     assert np.array_equal(steps, sref)    # per-point attempted steps bit-exact
     med, mx = _node_err(dx, ref)
+    record_parity(f"nodes[{name}]", per_node_median=med, per_node_max=mx, counters_equal=(c == cref), npts=n)
     assert med <= 1e-10 and mx <= 2e-6, (name, med, mx)
     assert st["launches"] >= 1 and st["local_bytes_per_thread"] <= 32  # at most the spill allowance of the residency choice
     # unweighted (MonteCarlo output_func, expectation.jl:282)
@@ -89,6 +91,8 @@ def test_reduce_mode_matches_oracle(gpu, name):
         # pdf-weighted reduction (the Koopman accumulators of SURVEY.md 8f rank 1)
         sw, s2w, cw = h.reduce_samples(x, weight_by_pdf=True)
     assert c == co and cw == co
+    record_parity(f"reduce[{name}]", sum_rel=float(np.max(np.abs(s - so) / np.abs(so))),
+                  sumsq_rel=float(np.max(np.abs(s2 - s2o) / np.abs(s2o))), counters_equal=(c == co), npts=n)
     assert np.max(np.abs(s - so) / np.abs(so)) < 1e-8          # north_star tolerance
     assert np.max(np.abs(s2 - s2o) / np.abs(s2o)) < 1e-8
     swo, s2wo, _ = orc.reduce_samples(x, weight_by_pdf=True)
@@ -184,6 +188,39 @@ def test_static_schedule_is_bit_reproducible_and_dynamic_agrees(gpu):
         assert c_d == c_a
         assert np.array_equal(nodes_dyn, nodes_static) and np.array_equal(steps_dyn, steps_static)
         assert np.max(np.abs(s_d - s_a) / np.abs(s_a)) < 1e-12 and np.max(np.abs(q_d - q_a) / np.abs(q_a)) < 1e-12
+
+
+def test_pageable_input_is_staged_through_pinned_mirrors(gpu):
+    """An ordinary (pageable) host array -- what Integrals / Cubature hand f!(dx, x, p), and any numpy array -- is
+    copied chunk by chunk into pinned mirrors of the ring slots by the library's copy pool (b200_expect.cu CopyPool)
+    instead of going through the driver's single-threaded bounce buffer.  Same bytes must reach the kernels: under
+    the static schedule the sums are bit-identical to the pinned-buffer and device-resident calls, in both layouts,
+    with more chunks than ring slots and a ragged last chunk; nodes mode returns identical columns."""
+    name = "lorenz63"
+    n = 300_007                                  # 6 doubles per point: 14.4 MB, 10 chunks of 32768 points
+    x = sample_points(name, n, seed=21)
+    assert x.nbytes >= 1 << 20
+    with gpu.Handle(gpu.models.builtin(name, schedule=1, chunk_points=32768)) as h:
+        xp = h.pinned((n, x.shape[1]))
+        xp.array[...] = x
+        a = h.reduce_samples(x)                  # pageable: staged
+        b = h.reduce_samples(xp)                 # pinned: direct DMA
+        assert h.last_stats()["launches"] >= 10
+        xs = np.ascontiguousarray(x.T)           # SoA rows of a pageable array
+        c = h.reduce_samples(xs, layout=1)
+        dx_page = h.eval_nodes(x, weight_by_pdf=True)
+        dx_pin = h.eval_nodes(xp, weight_by_pdf=True)
+        xp.free()
+    assert a[2] == b[2] == c[2]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
+    assert np.array_equal(dx_page, dx_pin)
+    orc = oracle.OracleProblem.builtin(name)
+    so, _, co = orc.reduce_samples(x[:50_000], nthreads=8)
+    with gpu.Handle(gpu.models.builtin(name, chunk_points=8192)) as h:
+        s, _, cc = h.reduce_samples(x[:50_000])  # 2.4 MB pageable, default (dynamic) schedule
+    _assert_counters_match_oracle(cc, co, 50_000)
+    assert np.max(np.abs(s - so) / np.abs(so)) < 1e-8
 
 
 @pytest.mark.parametrize("name", ALL)
@@ -381,6 +418,10 @@ def test_readme_koopman_through_public_api(gpu):
     ref = gpu.hcubature_v(lambda x: orc.eval_nodes(x, weight_by_pdf=True)[0], [1.0, 0.0], [10.0, 6.0], fdim=2,
                           reltol=1e-3, abstol=1e-3, record=rec_cpu)
     assert [len(b) for b in rec] == [17, 34, 68] and all(np.array_equal(a, b) for a, b in zip(rec, rec_cpu))
+    record_parity("koopman[README linear2, public API]", u_rel=float(np.max(np.abs(sol.u - ref.u) / np.abs(ref.u))),
+                  resid_rel=float(np.max(np.abs(sol.resid - ref.resid) / np.abs(ref.resid))),
+                  u_vs_readme_abs=float(np.max(np.abs(sol.u - np.array(README["koopman_u"])))),
+                  resid_vs_readme_abs=float(np.max(np.abs(sol.resid - np.array(README["koopman_resid"])))))
     assert np.max(np.abs(sol.u - ref.u) / np.abs(ref.u)) < 1e-8
     assert np.max(np.abs(sol.resid - ref.resid) / np.abs(ref.resid)) < 1e-8
     assert np.allclose(sol.u, README["koopman_u"], rtol=0, atol=2e-9)
@@ -416,9 +457,26 @@ def test_lotka_volterra_koopman_batched(gpu):
                               maxevals=200000, record=rec_g)
     assert [len(b) for b in rec_g] == [len(b) for b in rec_c] and all(len(b) % 57 == 0 for b in rec_g)
     assert all(np.array_equal(a, b) for a, b in zip(rec_g, rec_c))
+    record_parity("koopman[lotka_volterra, batched host driver]", u_rel=abs(got.u[0] - ref.u[0]) / abs(ref.u[0]),
+                  resid_rel=abs(got.resid[0] - ref.resid[0]) / abs(ref.resid[0]), nevals=int(got.nevals))
     assert abs(got.u[0] - ref.u[0]) / abs(ref.u[0]) < 1e-8
-    assert abs(got.resid[0] - ref.resid[0]) / abs(ref.resid[0]) < 1e-6   # resid is a difference of two rules
+    # resid = |I7 - I5| is a difference of two rules of size u (here resid = 3e-3 u): node-level rounding noise of
+    # relative size e in u shows up as e * u / resid in resid.  At the DEFAULT ODE tolerance (reltol 1e-3: the global
+    # error every implementation-dependent rounding of dt is multiplied with is ~1e-3) that noise is 3e-11 u, i.e.
+    # 1.1e-8 of resid (profiles/r2_parity_observed.json) -- the one place north_star's 1e-8 on resid is missed, by 10 %;
+    # the bar is 1e-8 relative plus that floor.  At a matched tolerance of 1e-8 the strict bar holds (next lines and
+    # test_koopman_solve_in_library_matches_host_driver).
+    assert abs(got.resid[0] - ref.resid[0]) <= 1e-8 * abs(ref.resid[0]) + 1e-10 * abs(ref.u[0])
     assert got.nevals == ref.nevals and got.converged == ref.converged
+    # the same solve at matched tight ODE tolerances: u and resid strictly within 1e-8 relative
+    orc8 = oracle.OracleProblem.builtin("lotka_volterra", abstol=1e-8, reltol=1e-8)
+    ref8 = gpu.hcubature_v(lambda x: orc8.eval_nodes(x, weight_by_pdf=True)[0], lb, ub, fdim=1, reltol=1e-3, abstol=1e-3, maxevals=60000)
+    with gpu.Handle(gpu.models.builtin("lotka_volterra", abstol=1e-8, reltol=1e-8)) as h:
+        got8 = gpu.hcubature_v(lambda x: h.eval_nodes(x, weight_by_pdf=True), lb, ub, fdim=1, reltol=1e-3, abstol=1e-3, maxevals=60000)
+    record_parity("koopman[lotka_volterra, batched host driver, ODE tol 1e-8]", u_rel=abs(got8.u[0] - ref8.u[0]) / abs(ref8.u[0]),
+                  resid_rel=abs(got8.resid[0] - ref8.resid[0]) / abs(ref8.resid[0]), nevals=int(got8.nevals))
+    assert got8.nevals == ref8.nevals
+    assert abs(got8.u[0] - ref8.u[0]) / abs(ref8.u[0]) < 1e-8 and abs(got8.resid[0] - ref8.resid[0]) / abs(ref8.resid[0]) < 1e-8
 
 
 def test_process_noise_koopman_vs_montecarlo(gpu):
@@ -504,9 +562,13 @@ def test_koopman_solve_in_library_matches_host_driver(gpu):
         with gpu.Handle(gpu.models.builtin(name, **kw)) as h:
             u, resid, st = h.koopman_solve(lb, ub, reltol=tol, abstol=tol, maxevals=400000)
         assert (st["nevals"], st["nrounds"], st["nregions"], bool(st["converged"])) == (ref.nevals, ref.nrounds, ref.nregions, ref.converged), (name, st)
+        record_parity(f"koopman_solve[{name}, tol {tol:g}]", u_rel=float(np.max(np.abs(u - ref.u) / np.abs(ref.u))),
+                      resid_rel=float(np.max(np.abs(resid - ref.resid) / np.abs(ref.resid))), nevals=int(st["nevals"]))
         assert np.max(np.abs(u - ref.u) / np.abs(ref.u)) < 1e-8, (name, u, ref.u)
-        # resid is a difference of two quadrature sums: its own floor is a few ulp of u
-        assert np.all(np.abs(resid - ref.resid) <= 1e-6 * np.abs(ref.resid) + 8 * np.finfo(float).eps * np.abs(ref.u)), (name, resid, ref.resid)
+        # north_star: resid within 1e-8 relative.  resid is a difference of two quadrature sums of size u, so a few
+        # ulp of u is its absolute floor whatever the implementation (decay1 converges to resid ~ 1e-10 u)
+        floor = 1e-10 if (name == "lotka_volterra" and not kw) else 8 * np.finfo(float).eps   # default ODE tolerance: see test_lotka_volterra_koopman_batched
+        assert np.all(np.abs(resid - ref.resid) <= 1e-8 * np.abs(ref.resid) + floor * np.abs(ref.u)), (name, resid, ref.resid)
         assert st["counters"]["nfail"] == 0 and st["counters"]["naccept"] > 0
         if name == "linear2":
             assert np.allclose(u, README["koopman_u"], rtol=0, atol=2e-9)
