@@ -74,8 +74,10 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        build()
-        L = C.CDLL(_LIB_PATH)
+        override = os.environ.get("B200E_ORACLE_LIB")   # an instrumented build (tests/test_sanitizers.py)
+        if not override:
+            build()
+        L = C.CDLL(override or _LIB_PATH)
         L.orc_logpdf.restype = C.c_double
         L.orc_logpdf.argtypes = [C.POINTER(PdfDim), C.c_int, C.POINTER(C.c_double)]
         L.orc_pdf.restype = C.c_double

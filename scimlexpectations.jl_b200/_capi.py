@@ -112,11 +112,12 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("B200E_LIB") or LIB_PATH     # B200E_LIB: the same variable the Julia shim reads
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python scimlexpectations.jl_b200/build.py` "
+            f"{path} is missing: build it with `python scimlexpectations.jl_b200/build.py` "
             "(or __graft_entry__.build()).  This package has no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     H = C.c_void_p
     L.b200e_abi_version.restype = C.c_int
     L.b200e_device_count.restype = C.c_int

@@ -83,7 +83,11 @@ inline unsigned __reduce_add_sync(unsigned, unsigned v) {
     return s;
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp->bar.arrive_and_wait(); }
+#ifdef EMU_DROP_BLOCK_BARRIER  // negative control of the ThreadSanitizer run: without the barrier it must report the race
+inline void __syncthreads() {}
+#else
 inline void __syncthreads() { emu_block_bar->arrive_and_wait(); }
+#endif
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 template <class T> inline T __ldg(const T *p) { return *p; }
