@@ -396,6 +396,7 @@ def in_library_legs(sme, args, world, rank, model, n, nx, x_rank0):
                                            "evals_per_s": total / min(times), "expectation": (s / total).tolist(),
                                            "nf": c["nf"], "nfail": c["nfail"]}
     dist.barrier(group=cpu_group)
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     return res
 
 

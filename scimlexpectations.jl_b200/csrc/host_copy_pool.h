@@ -69,7 +69,10 @@ private:
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof set, &set) == 0) hw = (unsigned)CPU_COUNT(&set);
         // measured on the 16-core B200 box, 160 MB per call (pinned: 3.07 ms): 4 copy streams 5.3 ms, 8 3.8 ms, 12 3.55 ms
-        int want = std::min(11, (int)hw * 3 / 4 - 1);  // + the caller
+        // one process per GPU (torchrun exports LOCAL_WORLD_SIZE): the ranks share the host's cores
+        int share = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) share = std::max(1, atoi(e));
+        int want = std::min(11, (int)hw * 3 / 4 / share - 1);  // + the caller
         if (const char *e = getenv("B200E_COPY_THREADS")) want = std::max(0, atoi(e) - 1);
         const int n = std::max(0, std::min<int>(want, (int)hw - 1));
         for (int w = 0; w < n; w++) workers_.emplace_back([this, w] { run(w); });

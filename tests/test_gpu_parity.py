@@ -510,11 +510,23 @@ def test_single_process_multi_device_sharding(gpu):
         d1 = h.eval_nodes(x)
         sg1, qg1, cg1 = h.reduce_generated(3, 300007, first_index=77)
     devs = list(range(min(nd, 8)))
+    import ctypes
+    rt = ctypes.CDLL(None)
+    cur = ctypes.c_int(-1)
+    have_rt = hasattr(rt, "cudaGetDevice")           # only when a shared cudart happens to be loaded (torch's)
     with gpu.Handle(gpu.models.builtin(name, devices=devs, chunk_points=50000)) as h:
         s, q, c = h.reduce_samples(x)
         d = h.eval_nodes(x)
         cn = h.last_counters()
         sg, qg, cg = h.reduce_generated(3, 300007, first_index=77)   # every device draws its own index range
+        # the caller's current device is put back by every entry point (the library hops over all its devices)
+        try:
+            import torch
+            assert torch.cuda.current_device() == 0
+        except ImportError:
+            if have_rt:
+                rt.cudaGetDevice(ctypes.byref(cur))
+                assert cur.value == 0
     assert c == c1 and cn == c1 and cg == cg1
     assert np.allclose(s, s1, rtol=1e-12) and np.allclose(q, q1, rtol=1e-12)
     assert np.allclose(sg, sg1, rtol=1e-12) and np.allclose(qg, qg1, rtol=1e-12)
