@@ -858,7 +858,17 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     block_reduce_store<REDUCE>(P, A);
 }
 
-extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_MINBLOCKS)
+// Under the dynamic schedules the static per-node kernel only runs launches with at most one point per lane -- the
+// Koopman refinement rounds, where a round costs one trajectory LATENCY, not throughput: it is compiled for half the
+// residency (twice the registers: no spills, a freer instruction schedule; lotka_volterra at tol 1e-8, 29 rounds:
+// 6.34 -> 5.57 ms of kernel time, profiles/r2_koopman_shapes.log).  With B200E_SCHED_STATIC it carries the large
+// batches as well and keeps the full residency.
+#if B200E_DYNAMIC
+#define B200E_NODES_MINBLOCKS ((B200E_MINBLOCKS + 1) / 2)
+#else
+#define B200E_NODES_MINBLOCKS B200E_MINBLOCKS
+#endif
+extern "C" __global__ void __launch_bounds__(B200E_BLOCK, B200E_NODES_MINBLOCKS)
 b200e_nodes(const __grid_constant__ b200e_kparams P) {
     tsit5_run<false, false, false>(P);
 }
