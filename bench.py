@@ -563,6 +563,12 @@ def run_b200(args):
     clocks = sampler.stop()
     e_steps = max(3, args.steps // 4)
     Te, _, e_total_ms, _, (se, s2e, ce, ste) = timed(step_e2e, e_steps, 3)
+    # the ceiling of every host-fed leg: plain cudaMemcpy of the rank's pinned buffer, all ranks at once
+    def step_h2d_only():
+        xd.upload(xp.array)
+        return None, None, None, {"kernel_ms": 0.0, "total_ms": 0.0, "launches": 0}
+    Th, _, _, _, _ = timed(step_h2d_only, e_steps, 2)
+    h2d_ceiling_gbs = world * n * nx * 8 * e_steps / Th / 1e9
     Tp, _, _, _, (sp_, _, cp_, stp) = timed(step_pageable, e_steps, 3)
     Tg, g_kernel_ms, _, _, (sg, s2g, cg, stg) = timed(step_generated, args.steps, 3)
     strong = strong_scaling_legs(sme, args, world, rank, local_rank, barrier)
@@ -606,7 +612,9 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(ste["h2d_bytes"]),
                     "d2h_bytes_per_step": int(ste["d2h_bytes"]), "ms_per_step": Te / e_steps * 1e3,
-                    "api": "b200e_reduce_samples(host pinned x) -> host sums"},
+                    "api": "b200e_reduce_samples(host pinned x) -> host sums",
+                    # what the host can feed at all: the same buffers through plain cudaMemcpy, every rank at once
+                    "h2d_ceiling_gbs": h2d_ceiling_gbs, "h2d_achieved_gbs": world * n * nx * 8 * e_steps / Te / 1e9},
             # not the contract's e2e (its inputs never exist on the host): the public MonteCarlo call with the
             # sampler inside the kernel, the configuration a user of solve(exprob, MonteCarlo(n)) runs
             # the same call from pageable host memory (a numpy array; Julia's Array handed to f!(dx, x, p))

@@ -80,7 +80,8 @@ enum { B200E_LAYOUT_POINT_MAJOR = 0, B200E_LAYOUT_SOA = 1 };
  * equal pace).  Per-node outputs and all integer counters are identical under both; the floating-point
  * SUMS of b200e_reduce_samples are accumulated per lane, so under DYNAMIC their last bits depend on the
  * run-time assignment (differences ~1e-16 relative).  STATIC: lane l owns points l, l+T, l+2T, ...;
- * sums are bit-reproducible for a given launch shape.  DYNAMIC_REPRODUCIBLE (end-state observables): warps take super-chunks of consecutive points, sum each chunk of 32 with a fixed shuffle tree and
+ * sums are bit-reproducible for a given launch shape.  DYNAMIC_REPRODUCIBLE (end-state and time-sampled observables):
+ * warps take super-chunks of consecutive points, sum each chunk of 32 with a fixed shuffle tree and
  * write one row of sums per super-chunk; the rows are folded in index order.  Sums are bit-reproducible and do
  * not depend on the launch shape either, at the price of always starting 32 trajectories together. */
 enum { B200E_SCHED_DYNAMIC = 0, B200E_SCHED_STATIC = 1, B200E_SCHED_DYNAMIC_REPRODUCIBLE = 2 };

@@ -726,7 +726,7 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     // writes ONE row of sums per super-chunk.  A row is a function of the points of its super-chunk only
     // and the rows are folded in index order afterwards: the result does not depend on which warp solved
     // what, nor on the launch shape.
-    constexpr bool repro = B200E_REPRO && REDUCE && DYN && B200E_NSAVE == 0;
+    constexpr bool repro = B200E_REPRO && REDUCE && DYN;
     __shared__ double sh_wacc[repro ? NWARPS : 1][repro ? NACC : 1];
     long long sc_next = 0, sc_row = -1;
     int sc_left = 0;
@@ -754,7 +754,23 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 if (mx * 128u > sm * 5u) thr_eff = 8;  // max > 1.25 * mean
                 tune = false;
             }
-#if B200E_NSAVE == 0
+#if B200E_NSAVE > 0
+            if (repro && done_m != 0u) {
+                // time-sampled observables: the accept branch has put the (weighted) slot values of the lane's ONE
+                // trajectory of this chunk, and their squares, into the lane's accumulator columns (unused otherwise
+                // under this schedule); aborted trajectories add their NaN slots now.  Chunk sums in a fixed order,
+                // then the columns are cleared for the next chunk.
+                if (L.state == LANE_DONE) emit_missing<REDUCE>(P, cur, L.ksave, wgt, A);
+#pragma unroll 1
+                for (int k = 0; k < NACC; k++) {
+                    double v = A.val(k);
+                    A.val(k) = 0.0;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(B200E_FULL, v, off);
+                    if ((threadIdx.x & 31) == 0) sh_wacc[threadIdx.x >> 5][k] += v;
+                }
+            }
+#else
             if (repro && done_m != 0u) {
                 // chunk sum in a fixed order: lanes without a point contribute zeros
                 real out[NOUT];
@@ -780,7 +796,7 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
 #endif
             if (L.state == LANE_DONE) {
 #if B200E_NSAVE > 0
-                emit_missing<REDUCE>(P, cur, L.ksave, wgt, A);
+                if (!repro) emit_missing<REDUCE>(P, cur, L.ksave, wgt, A);
 #else
                 if (!repro) emit<REDUCE>(P, cur, L.u, L.p, wgt, A);
 #endif

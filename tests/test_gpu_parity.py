@@ -714,8 +714,29 @@ def test_reproducible_dynamic_schedule(gpu):
             t1, t2 = h.reduce_generated(6, 1000), h.reduce_generated(6, 1000)
             w1, w2 = h.reduce_samples(x[:1000]), h.reduce_samples(x[:1000])
         assert np.array_equal(t1[0], t2[0]) and t1[2] == t2[2] and np.array_equal(w1[0], w2[0]) and w1[2] == w2[2]
-    with pytest.raises(gpu.B200Error):   # end-state observables only
-        gpu.Handle(gpu.models.builtin("linear2_saveat", schedule=2))
+    # time-sampled observables (saveat) under the same schedule: slot sums bit-identical across runs and launch shapes,
+    # equal to the plain dynamic schedule's to summation-order rounding, counters as always
+    name = "linear2_saveat"
+    n = 300007
+    x = sample_points(name, n, seed=52)
+    ref = None
+    for shape in (dict(block_size=64, blocks_per_sm=2), dict(block_size=128, blocks_per_sm=3)):
+        with gpu.Handle(gpu.models.builtin(name, schedule=2, **shape)) as h:
+            d = h.device_array(x.shape).upload(x)
+            a, b = h.reduce_samples(d, npts=n), h.reduce_samples(d, npts=n)
+            g1 = h.reduce_generated(6, n)
+            d.free()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+        if ref is None:
+            ref = (a, g1)
+        else:
+            assert np.array_equal(a[0], ref[0][0]) and np.array_equal(a[1], ref[0][1]) and a[2] == ref[0][2]
+            assert np.array_equal(g1[0], ref[1][0]) and g1[2] == ref[1][2]
+    with gpu.Handle(gpu.models.builtin(name)) as h:
+        s, q, c = h.reduce_samples(x)
+    assert c == ref[0][2]
+    scale = np.abs(s).max()
+    assert np.max(np.abs(s - ref[0][0])) < 1e-12 * scale and np.max(np.abs(q - ref[0][1])) < 1e-12 * np.abs(q).max()
 
 
 def test_full_size_properties_through_the_in_kernel_sampler(gpu):
@@ -852,3 +873,72 @@ def test_reference_solve_testset(gpu, nout):
     with pytest.raises(NotImplementedError):       # the unbatched integrand stays on the reference's CPU path
         gpu.solve(ex, gpu.Koopman(), quadalg=gpu.CubatureJLh())
     ex.close()
+
+
+def test_distinct_handles_from_distinct_threads(gpu):
+    """Threading contract of the boundary (include/b200_expect.h): calls on one handle are serialised by the caller,
+    distinct handles may be used from distinct threads.  Four threads, each with its own handle (two models), run
+    pageable-input reductions (the shared staging pool), node batches and in-library Koopman solves at the same time;
+    every result equals the one the same call gives alone."""
+    import threading
+    jobs = [("linear2", 21), ("lorenz63", 22), ("linear2", 23), ("lorenz63", 24)]
+    data = {seed: sample_points(name, 150_001, seed=seed) for name, seed in jobs}
+    alone = {}
+    for name, seed in jobs:
+        with gpu.Handle(gpu.models.builtin(name, schedule=1, chunk_points=32768)) as h:
+            alone[seed] = (h.reduce_samples(data[seed]), h.eval_nodes(data[seed][:20_000]))
+    got, errors = {}, []
+
+    def work(name, seed):
+        try:
+            with gpu.Handle(gpu.models.builtin(name, schedule=1, chunk_points=32768)) as h:
+                for _ in range(3):
+                    r = h.reduce_samples(data[seed])
+                    d = h.eval_nodes(data[seed][:20_000])
+                    if name == "linear2":
+                        u, resid, st = h.koopman_solve([1.0, 0.0], [10.0, 6.0], reltol=1e-3, abstol=1e-3)
+                        assert st["nevals"] == 119 and np.allclose(u, README["koopman_u"], rtol=0, atol=2e-9)
+                got[seed] = (r, d)
+        except Exception as e:  # noqa: BLE001
+            errors.append((seed, repr(e)))
+
+    threads = [threading.Thread(target=work, args=j) for j in jobs]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for _, seed in jobs:
+        (s, q, c), d = got[seed]
+        (s0, q0, c0), d0 = alone[seed]
+        assert c == c0 and np.array_equal(s, s0) and np.array_equal(q, q0) and np.array_equal(d, d0)
+
+
+def test_handles_release_their_device_memory(gpu):
+    """b200e_destroy gives back everything a handle took -- module, streams, ring slots, pinned staging mirrors, the
+    second reduction slot, the cubature buffers: 40 create / use / destroy cycles (what 40 Koopman + MonteCarlo solves
+    through a shim without a handle cache would do) leave the device's free memory where it was."""
+    torch = pytest.importorskip("torch")
+    name = "linear2"
+    x = sample_points(name, 200_000, seed=61)
+
+    def cycle():
+        with gpu.Handle(gpu.models.builtin(name)) as h:
+            h.reduce_samples(x)                                    # ring + staging mirrors
+            d = h.device_array(x.shape).upload(x)
+            h.reduce_samples_begin(d, npts=len(x)); h.reduce_samples_begin(d, npts=len(x))
+            h.reduce_samples_end(); h.reduce_samples_end()         # second reduction slot
+            d.free()
+            h.eval_nodes(x[:5000])
+            h.koopman_solve([1.0, 0.0], [10.0, 6.0], reltol=1e-3, abstol=1e-3)
+            h.reduce_generated(1, 100_000)
+
+    for _ in range(3):
+        cycle()                                                     # context, module cache, allocator pools settle
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(40):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 8 << 20, (free0, free1)                  # a leak of one ring slot per cycle would be 128 MB

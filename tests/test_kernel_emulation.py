@@ -174,6 +174,15 @@ def test_time_sampled_observable_kernel_on_the_cpu(sme, tmp_path):
     so, s2o, co = orc.reduce_samples(x)
     _, _, s, s2, c, _ = _run(exe, spec, tmp, x, "reduce", weight=0, grid=2)
     _check_sums(s, s2, c, so, s2o, co)
+    # the reproducible dynamic schedule with time-sampled observables: the lane's slot values of a chunk are summed
+    # over the lanes in a fixed order at the end of the chunk; bit-identical rows for one and three blocks
+    exe_r = _build(sme, spec.replace(schedule=2), tmp, repro=1)
+    got = []
+    for grid in (1, 3):
+        _, _, s, s2, c, _ = _run(exe_r, spec, tmp, x, "reduce_dyn", weight=0, grid=grid)
+        _check_sums(s, s2, c, so, s2o, co)
+        got.append((s.copy(), s2.copy()))
+    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
 
 
 @pytest.mark.parametrize("family,seed", [("ode", 1), ("ode", 6), ("ode", 16), ("noise", 0), ("noise", 4), ("noise", 7)])
