@@ -1,0 +1,4 @@
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/r2_pytest_gpu.log
+cp gpurun_out/parity_observed.json gpurun_out/r2_parity_observed_full.json
