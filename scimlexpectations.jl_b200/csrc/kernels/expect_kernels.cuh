@@ -926,6 +926,9 @@ constexpr int NK = B200E_NKKL;
 #ifndef B200E_EM_SPT
 #define B200E_EM_SPT 2
 #endif
+#ifndef B200E_EM_PREFETCH
+#define B200E_EM_PREFETCH 1
+#endif
 constexpr int SPT = B200E_EM_SPT;
 
 template <bool REDUCE, bool DYN, bool GEN>
@@ -994,8 +997,9 @@ __device__ __forceinline__ void em_run(const b200e_kparams &P) {
         // shared by the lane's SPT samples).  Step times as in the oracle, t_n = t0 + n h with t_N = t1, from
         // a floating-point counter (an int64 -> double conversion per step costs more than the whole drift).
         const double *tab = P.kkl_table;
-        real row[NK], wcur[SPT];
-        auto load_row = [&](const double *r) {
+        real wcur[SPT];
+        auto load_row = [&](real *row, long long idx) {
+            const double *r = tab + idx * NK;
             if (NK % 2 == 0) {
                 const double2 *r2 = reinterpret_cast<const double2 *>(r);
 #pragma unroll
@@ -1009,25 +1013,22 @@ __device__ __forceinline__ void em_run(const b200e_kparams &P) {
                 for (int k = 0; k < NK; k++) row[k] = (real)__ldg(r + k);
             }
         };
-        auto kkl_dot = [&](const real *zq) {
+        auto kkl_dot = [&](const real *zq, const real *row) {
             real w = (real)0;
 #pragma unroll
             for (int k = 0; k < NK; k++) w = fma(zq[k], row[k], w);
             return w;
         };
-        load_row(tab);
-#pragma unroll
-        for (int q = 0; q < SPT; q++) wcur[q] = kkl_dot(z[q]);
         const int ns = (int)nsteps;
         real t = t0, sd = (real)0;
-        for (int s = 0; s < ns; s++) {
+        // one Euler-Maruyama step of the lane's SPT samples with the table row of t_{s+1}
+        auto advance = [&](const real *row, int s) {
             sd += (real)1;
             const real tn = (s + 1 == ns) ? t1 : fma(sd, h, t0);
             const real dt = tn - t;
-            load_row(tab + (long long)(s + 1) * NK);
 #pragma unroll
             for (int q = 0; q < SPT; q++) {
-                const real wn = kkl_dot(z[q]);
+                const real wn = kkl_dot(z[q], row);
                 const real dW = wn - wcur[q];
                 wcur[q] = wn;
                 real f[N], g[N];
@@ -1037,7 +1038,30 @@ __device__ __forceinline__ void em_run(const b200e_kparams &P) {
                 for (int j = 0; j < N; j++) u[q][j] = fma(g[j], dW, fma(dt, f[j], u[q][j]));
             }
             t = tn;
+        };
+        real rowA[NK];
+        load_row(rowA, 0);
+#pragma unroll
+        for (int q = 0; q < SPT; q++) wcur[q] = kkl_dot(z[q], rowA);
+#if B200E_EM_PREFETCH
+        // two-stage software pipeline over the steps: the row of step s + 2 is requested before step s is computed,
+        // so its L1 latency is covered by a whole step of arithmetic (the warp count is low here: registers)
+        real rowB[NK];
+        load_row(rowA, ns < 1 ? 0 : 1);
+        int s = 0;
+        for (; s + 1 < ns; s += 2) {
+            load_row(rowB, s + 2);
+            advance(rowA, s);
+            load_row(rowA, s + 3 < ns ? s + 3 : ns);
+            advance(rowB, s + 1);
         }
+        if (s < ns) advance(rowA, s);
+#else
+        for (int s = 0; s < ns; s++) {
+            load_row(rowA, s + 1);
+            advance(rowA, s);
+        }
+#endif
 #pragma unroll
         for (int q = 0; q < SPT; q++) {
             if (repro) {  // chunk sum in a fixed order: lanes without a point contribute zeros
