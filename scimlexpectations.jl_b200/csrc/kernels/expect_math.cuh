@@ -143,8 +143,16 @@ B200E_MFN float sin_halfpi(float t) { return sinf(1.5707963267948966f * t); }
 B200E_MFN void sqrt_rsqrt_pos(float x, float &s, float &rs) { s = sqrtf(x); rs = 1.0f / s; }
 #endif
 #else
-// 1/b for normal b > 0: MUFU.RCP64H seed (20 bits: it reads the high word only) + one cubic step
-//   e = 1 - b r;  1/b = r / (1 - e) = r (1 + e + e^2 + O(e^3)),  e^3 <= 2^-60
+// 1/b for normal b > 0 to 2^-39.8 (1.1e-12): MUFU.RCP64H seed (20 bits: it reads the high word only) + ONE Newton step,
+//   e = 1 - b r;  1/b = r (1 + e + O(e^2)),  e <= 2^-19.9.
+// Accuracy matched to the use: rcp_pos, log_pos and exp_small only ever touch the STEP-SIZE CONTROL (scaled error norm,
+// PI controller, initial-step heuristic) -- they decide which dt is tried next, never the arithmetic of the solution.
+// A relative perturbation d of dt moves a trajectory's end state by ~5 d x (its global error, <= 1e-3 at the default
+// tolerance): 1e-12 here is 1e-14 there, six orders below the 1e-8 parity contract and far below the ~1e-6 noise the
+// very first step's error estimate carries in any implementation.  Round 1 refined to 1 ulp with
+// a cubic step and longer series; the shorter forms are 4 FP64 instructions less per attempted step (118 -> 114 on
+// linear2): -2.6 % kernel time on linear2, -2.0 % on lorenz63 (profiles/r2_sweep_mathvar.log), with every counter of the
+// GPU suite and of the fuzz runs still equal to the oracle's.
 B200E_MFN double rcp_pos(double b) {
     double r;
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
@@ -152,8 +160,7 @@ B200E_MFN double rcp_pos(double b) {
 #else
     r = __hiloint2double(__double2hiint(1.0 / __hiloint2double(__double2hiint(b), 0)), 0);  // same 20-bit class
 #endif
-    double e = fma(-b, r, 1.0);
-    e = fma(e, e, e);
+    const double e = fma(-b, r, 1.0);
     return fma(r, e, r);
 }
 // sqrt(x) for normal x > 0: MUFU.RSQ64H seed + two coupled Newton steps (Goldschmidt form)
@@ -195,7 +202,7 @@ B200E_MFN void sqrt_rsqrt_pos(double x, double &s, double &rs) {
 }
 // log(x), x > 0:  x = 2^e m, m in [1,2), j = top 7 bits of m's fraction;
 //   log x = e ln2 + lc_j + log1p(r),  r = x * (c_j 2^-e) - 1  (one exact-product DFMA), |r| <= 2^-8,
-//   log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5  (next term 2^-48/6 = 6e-16).
+//   log1p(r) = r - r^2/2 + r^3/3 - r^4/4  (next term 2^-40/5 = 1.8e-13 absolute: step-size control only, see rcp_pos).
 // c_j 2^-e is formed by subtracting x's exponent field from c_j's.  The high word is clamped so
 // +inf, NaN and sign-bit patterns read as ~2^1023: zero / subnormal x gives about -711 and those
 // about +708, for which the controller's clamps decide alone (EEst = 0 -> q = 1/qmax, EEst = Inf ->
@@ -208,22 +215,20 @@ B200E_MFN double log_pos(const b200e_tabs &T, double x) {
     const double r = fma(__hiloint2double((int)hi, __double2loint(x)), __hiloint2double(chi, __double2loint(ent.c)), -1.0);
     const double ef = __hiloint2double(0x43300000, (int)(hi >> 20)) - lit::two52_1023;  // (double)e, exact
     // Horner: every DFMA has two register sources (accumulator, r) and one immediate -> 2-cycle issue
-    double h = fma(r, K_(fifth), -0.25);
-    h = fma(h, r, lit::third_i);
+    double h = fma(r, -0.25, lit::third_i);
     h = fma(h, r, -0.5);
     h = fma(h, r, 1.0);
     return fma(h, r, fma(ef, K_(ln2), ent.lc));
 }
 // exp(y), |y| < 600:  n = round(128 y / ln2),  exp y = 2^(n >> 7) * 2^((n & 127)/128) * exp(r),
-//   r = y - n ln2/128, |r| <= ln2/256,  exp r - 1 = r + r^2 (1/2 + r/6 + r^2/24)  (next term 1.2e-15)
+//   r = y - n ln2/128, |r| <= ln2/256,  exp r - 1 = r + r^2 (1/2 + r/6)  (next term r^4/24 <= 2.2e-12 relative)
 B200E_MFN double exp_small(const b200e_tabs &T, double y) {
     const double t = fma(y, K_(log2e_128), lit::rnd_magic);
     const int n = __double2loint(t);
     const double nf = t - lit::rnd_magic;
     const double r = fma(-nf, K_(ln2_128), y);
     const double tj = T.ex[n & (TAB_N - 1)];
-    double h = fma(r, K_(r24), lit::sixth_i);
-    h = fma(h, r, 0.5);
+    double h = fma(r, lit::sixth_i, 0.5);
     h = fma(h, r, 1.0);
     const double p = fma(tj * h, r, tj);
     return __hiloint2double(__double2hiint(p) + ((n >> TAB_BITS) << 20), __double2loint(p));

@@ -90,11 +90,14 @@ def twin(tmp_path_factory):
 
 def test_table_log_exp_rcp_sqrt_accuracy(twin):
     maxl, maxe, maxr, maxs, maxpow = (float(v) for v in twin[0].split())
-    assert maxl < 3e-14      # absolute; 1.4e-14 is one ulp of |log x| = 80
-    assert maxe < 1e-14      # relative
-    assert maxr < 4e-16
+    # accuracy matched to the use (step-size control only, expect_math.cuh rcp_pos): series and Newton steps stop at
+    # ~1e-12; the test pins those levels from above AND from below (a silent return to the long forms, or a further cut,
+    # both show)
+    assert 1e-14 < maxl < 2.5e-13    # absolute: the dropped term r^5 / 5, |r| <= 2^-8
+    assert 1e-13 < maxe < 3e-12      # relative: the dropped term r^4 / 24, |r| <= ln2 / 256
+    assert 1e-14 < maxr < 1.2e-12    # (2^-19.9)^2 after one Newton step on the 20-bit seed
     assert maxs < 4e-16
-    assert maxpow < 1e-14    # the controller factor against two libm pow calls
+    assert maxpow < 3.5e-12          # the controller factor against two libm pow calls
 
 
 def test_log_is_finite_and_saturates_for_special_values(twin):
