@@ -352,7 +352,7 @@ struct Lane {
     real u[N], k1[N], p[B200E_DIM(NP)];
     real t, dt, le2old;
     int state;
-    int failed;  // 0 ok, 1 aborted, 2 NaN error estimate seen: abort at the next loop header
+    int failed;  // 0 ok, 1 aborted
     unsigned nf0, nacc, nrej;  // nf = nf0 (initial-step evaluations) + 6 * (nacc + nrej)
     int ksave;                 // time-sampled observables: next save slot
 };
@@ -375,7 +375,7 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     // below the resolution of t abort the trajectory (dt <= dtmax holds where dt is proposed) ----
     const real dt = pmin(L.dt, t1 - t);  // clip to the end point
     const real tnext = t + dt;
-    if (L.failed || (int)(L.nacc + L.nrej) >= maxiters || same_value(tnext, t)) {
+    if ((int)(L.nacc + L.nrej) >= maxiters || same_value(tnext, t)) {  // (a NaN estimate left dt = 0: tnext == t)
         L.failed = 1;
         L.state = LANE_DONE;
         return;
@@ -485,17 +485,19 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
 #endif
     if (accept) {
         L.le2old = max_with_negative(le2, R_(lit::le2_qoldinit));  // qold = max(EEst, 1e-4); le2 is never NaN
+        // fixed_t_for_floatingpoint_error! (|t_new - t1| < 100 ulp snaps to t1) and the loop condition !(t < t1) in
+        // one test: t1 - t_new < snap_tol, negative values included (the time of a finished trajectory is not used)
         const real left = t1 - tnext;
-        const bool snap = lt_nonneg(abs_bits(left), snap_tol);  // fixed_t_for_floatingpoint_error!
-        L.t = snap ? t1 : tnext;
+        const bool done = lt_any_pos(left, snap_tol);
+        L.t = done ? t1 : tnext;
 #pragma unroll
         for (int i = 0; i < N; i++) { u[i] = un[i]; k1[i] = k7[i]; }
         L.nacc++;
-        if (snap || is_negative(left)) L.state = LANE_DONE;  // !(t < t1); left == 0 snaps
+        if (done) L.state = LANE_DONE;
     } else {
         // NaN estimate: the reference counts a rejection, dt turns NaN and the solve aborts at the next
-        // loop header -- same here through L.failed = 2 (tested on this rarely taken side only)
-        L.failed = (e2 == e2) ? 0 : 2;
+        // loop header -- same here through dt = 0 (t + dt == t aborts there; tested on this rarely taken side only)
+        if (!(e2 == e2)) L.dt = R_(0.0);
         L.nrej++;
     }
 }
@@ -614,7 +616,7 @@ __device__ __forceinline__ void lamba_step(Lane &L, const real t1, const real dt
     const real t = L.t;
     const real dt = pmin(L.dt, t1 - t);  // modify_dt_for_tstops!
     const real tnext = t + dt;
-    if (L.failed || (int)(L.nacc + L.nrej) >= maxiters || same_value(tnext, t)) {
+    if ((int)(L.nacc + L.nrej) >= maxiters || same_value(tnext, t)) {  // (a NaN estimate left dt = 0: tnext == t)
         L.failed = 1;
         L.state = LANE_DONE;
         return;
@@ -657,15 +659,15 @@ __device__ __forceinline__ void lamba_step(Lane &L, const real t1, const real dt
     if (accept) {
         L.le2old = max_with_negative(le2, R_(lit::le2_qoldinit));
         const real left = t1 - tnext;
-        const bool snap = lt_nonneg(abs_bits(left), snap_tol);  // fixed_t_for_floatingpoint_error!
-        L.t = snap ? t1 : tnext;
+        const bool done = lt_any_pos(left, snap_tol);  // fixed_t_for_floatingpoint_error! and !(t < t1), see tsit5_step
+        L.t = done ? t1 : tnext;
 #pragma unroll
         for (int i = 0; i < N; i++) u[i] = un[i];
         L.wcur = wn;
         L.nacc++;
-        if (snap || is_negative(left)) L.state = LANE_DONE;
+        if (done) L.state = LANE_DONE;
     } else {
-        L.failed = (e2 == e2) ? 0 : 2;
+        if (!(e2 == e2)) L.dt = R_(0.0);   // NaN estimate: abort at the next loop header
         L.nrej++;
     }
 }
@@ -862,14 +864,16 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
             act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
         }
         if (act_m == 0u) continue;
-        // ---- step phase: a tight loop, one vote per step, until some lane finishes ----
+        // ---- step phase: a tight loop, one vote per step, until some lane finishes (a lane only ever goes from
+        // ACTIVE to DONE in here, so "nobody finished" is one all-vote on a per-lane predicate) ----
+        const bool stepping = L.state == LANE_ACTIVE;
         do {
 #if B200E_SOLVER == 2
             if (L.state == LANE_ACTIVE) lamba_step<REDUCE>(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps);
 #else
             if (L.state == LANE_ACTIVE) tsit5_step<REDUCE>(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps, SaveCtx{P, cur, wgt, A});
 #endif
-        } while (__ballot_sync(B200E_FULL, L.state == LANE_ACTIVE) == act_m);
+        } while (__all_sync(B200E_FULL, !stepping || L.state == LANE_ACTIVE));
     }
     block_reduce_store<REDUCE>(P, A);
 }

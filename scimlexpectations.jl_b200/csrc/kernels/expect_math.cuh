@@ -273,6 +273,7 @@ B200E_MFN bool same_value(float a, float b) { return a == b; }
 B200E_MFN bool le_nonneg(float a, float b) { return a <= b; }
 B200E_MFN bool lt_nonneg(float a, float b) { return a < b; }
 B200E_MFN bool is_negative(float a) { return a < 0.0f; }
+B200E_MFN bool lt_any_pos(float a, float b) { return a < b; }
 B200E_MFN float max_with_negative(float a, float q) { return fmaxf(a, q); }
 #elif defined(__CUDACC__) || defined(__CUDACC_RTC__)
 // |x| through the sign bit (an ALU LOP3; fabs of a double is a DADD on the FP64 pipe)
@@ -293,6 +294,10 @@ B200E_MFN bool lt_nonneg(double a, double b) {
     return (unsigned long long)__double_as_longlong(a) < (unsigned long long)__double_as_longlong(b);
 }
 B200E_MFN bool is_negative(double a) { return __double2hiint(a) < 0; }  // sign bit (true for -0.0)
+// a < b for any non-NaN a and a POSITIVE b, as ONE signed 64-bit integer compare of the bit patterns: a pattern with the
+// sign bit set is a negative integer (so every negative a, -0.0 included, compares below b), and for a >= 0 the IEEE
+// order is the integer order
+B200E_MFN bool lt_any_pos(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
 // max(a, q) for finite a and a NEGATIVE constant q: a >= 0 has the smaller unsigned pattern (no sign
 // bit), and of two negative values the smaller pattern is the smaller magnitude, i.e. the larger value
 B200E_MFN double max_with_negative(double a, double q) {

@@ -66,6 +66,7 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
     emu_warp->bar.arrive_and_wait();
     return m;
 }
+inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 inline unsigned __reduce_max_sync(unsigned, unsigned v) {
     emu_warp->slot[emu_lane] = v;
     emu_warp->bar.arrive_and_wait();

@@ -25,6 +25,7 @@ inline bool same_value(double a, double b) { return __double_as_longlong(a) == _
 inline bool le_nonneg(double a, double b) { return (unsigned long long)__double_as_longlong(a) <= (unsigned long long)__double_as_longlong(b); }
 inline bool lt_nonneg(double a, double b) { return (unsigned long long)__double_as_longlong(a) < (unsigned long long)__double_as_longlong(b); }
 inline bool is_negative(double a) { return __double_as_longlong(a) < 0; }
+inline bool lt_any_pos(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
 inline double max_with_negative(double a, double q) {
     return __longlong_as_double((long long)std::min((unsigned long long)__double_as_longlong(a), (unsigned long long)__double_as_longlong(q)));
 }
