@@ -671,7 +671,7 @@ def test_larger_state_dimension(gpu):
         s, s2, cr = h.reduce_samples(x)
         raw = h.eval_nodes(x, weight_by_pdf=False)
     assert c == cref == cr and np.array_equal(steps, sref)
-    assert st["regs_per_thread"] == 128 and st["blocks_per_sm_occ"] * st["block"] == 512   # 16 resident warps per SM
+    assert 120 <= st["regs_per_thread"] <= 128 and st["blocks_per_sm_occ"] * st["block"] == 512   # 16 resident warps per SM
     med, mx = _node_err(dx, ref)
     assert med <= 1e-10 and mx <= 2e-6
     assert np.max(np.abs(s - so) / np.abs(so)) < 1e-8
