@@ -85,7 +85,8 @@ enum { B200E_LAYOUT_POINT_MAJOR = 0, B200E_LAYOUT_SOA = 1 };
  * write one row of sums per super-chunk; the rows are folded in index order.  Sums are bit-reproducible and do
  * not depend on the launch shape either, at the price of always starting 32 trajectories together. */
 enum { B200E_SCHED_DYNAMIC = 0, B200E_SCHED_STATIC = 1, B200E_SCHED_DYNAMIC_REPRODUCIBLE = 2 };
-enum { B200E_PDF_NONE = 0, B200E_PDF_UNIFORM = 1, B200E_PDF_NORMAL = 2, B200E_PDF_TRUNCNORMAL = 3, B200E_PDF_TABLE = 4 };
+enum { B200E_PDF_NONE = 0, B200E_PDF_UNIFORM = 1, B200E_PDF_NORMAL = 2, B200E_PDF_TRUNCNORMAL = 3, B200E_PDF_TABLE = 4,
+       B200E_PDF_LOGPOLY = 5 };
 
 /* one factor of GenericDistribution(dists...) (src/distribution_utils.jl:40-48) */
 typedef struct {
@@ -99,6 +100,13 @@ typedef struct {
      * [lo, hi]  (docs/src/tutorials/gpu_bayesian.md:153-166: pdf_func(x) = prod(pdf.(p_kde, x)), lb / ub = the grid
      * ends).  b200e_create prefilters the values into spline coefficients on the host and copies those; the kernel
      * evaluates three taps.  Koopman only: a tabulated factor cannot be sampled. */
+    /* B200E_PDF_LOGPOLY: any factor whose log-density on [lo, hi] is
+     *     logpdf(x) = c0 + c1 x + c2 x^2 + c3 log(x) + c4 log(1 - x) + c5 log(x)^2          (-inf outside [lo, hi])
+     * -- Exponential, Gamma / Chi-squared / Erlang, Beta, LogNormal, Rayleigh, Normal, and truncated(...) of any of them
+     * with log(cdf(hi) - cdf(lo)) folded into c0 by the caller (Distributions.logpdf semantics behind
+     * src/distribution_utils.jl:42).  `table` points to the six coefficients c0 .. c5, `ntable` = 6; lo / hi may be
+     * infinite (a MonteCarlo model; a Koopman solve needs a finite box).  Like a tabulated factor it cannot be drawn by
+     * the in-kernel sampler: MonteCarlo ships host samples for such a model. */
     const double *table;
     int64_t ntable;
 } b200e_pdf_dim;

@@ -105,7 +105,30 @@ pdfdim(d::Normal) = PdfDim(2, 0, -Inf, Inf, mean(d), std(d), C_NULL, 0)
 pdfdim(d::Truncated{<:Normal}) = PdfDim(3, 0, minimum(d), maximum(d), mean(d.untruncated), std(d.untruncated), C_NULL, 0)
 # a KernelDensity.UnivariateKDE (gpu_bayesian.md:153-166); `k.density` must stay alive until b200e_create returns
 pdfdim(k::KernelDensity.UnivariateKDE) = PdfDim(4, 0, first(k.x), last(k.x), 0.0, 1.0, pointer(k.density), length(k.density))
-pdfdim(d) = error("B200Expectations: no device pdf table for $(typeof(d)); supported: Uniform, Normal, truncated(Normal), KernelDensity.UnivariateKDE")
+pdfdim(d) = error("B200Expectations: no device pdf table for $(typeof(d)); supported: Uniform, Normal, truncated(Normal), " *
+                  "Exponential, Gamma, Beta, LogNormal and their truncations, KernelDensity.UnivariateKDE")
+
+# Log-polynomial factors (B200E_PDF_LOGPOLY): logpdf = c0 + c1 x + c2 x^2 + c3 log x + c4 log(1 - x) + c5 log(x)^2 on the
+# support.  `logpoly_shape` gives c1 .. c5; c0 (the normaliser, and log(tp) of a truncation) is read off Distributions'
+# own logpdf at an interior point, so no special function is restated here.
+logpoly_shape(d) = nothing
+logpoly_shape(d::Exponential) = (-1 / scale(d), 0.0, 0.0, 0.0, 0.0)
+logpoly_shape(d::Gamma) = (-1 / scale(d), 0.0, shape(d) - 1, 0.0, 0.0)
+logpoly_shape(d::Beta) = (0.0, 0.0, params(d)[1] - 1, params(d)[2] - 1, 0.0)
+logpoly_shape(d::LogNormal) = (0.0, 0.0, params(d)[1] / params(d)[2]^2 - 1, 0.0, -1 / (2 * params(d)[2]^2))
+logpoly_shape(d::Truncated) = d.untruncated isa Normal ? nothing : logpoly_shape(d.untruncated)
+function logpoly(d)
+    s = logpoly_shape(d)
+    s === nothing && return nothing
+    x = quantile(d, 0.5)
+    c0 = logpdf(d, x) - (s[1] * x + s[2] * x^2 + s[3] * log(x) + (s[4] == 0 ? 0.0 : s[4] * log1p(-x)) + s[5] * log(x)^2)
+    return Float64[c0, s...]
+end
+# `c` must stay alive until b200e_create returns (create_handle preserves it)
+pdfdim(d, c::Vector{Float64}) = PdfDim(5, 0, minimum(d), maximum(d), 0.0, 1.0, pointer(c), 6)
+pdfdim(d, ::Nothing) = pdfdim(d)
+"true when the kernel's sampler can draw `rand(d)` itself (an inverse CDF in closed form)"
+device_samplable(d) = d isa Uniform || d isa Normal || (d isa Truncated && d.untruncated isa Normal)
 
 # what identifies a factor in the handle cache (a KDE by its grid ends and a digest of its values, not by identity)
 factor_key(d) = d
@@ -134,13 +157,14 @@ function create_handle(prob, ens::EnsembleB200, kw, dists; solver = 0, n_kkl = 0
                 map(factor_key, Tuple(dists)), m.rhs, m.diffusion, m.hmap, m.observable, m.nout, ens.fp32, ens.schedule, ens.devices))
     cached = get(ens.cache, key, nothing)
     cached === nothing || cached.ptr == C_NULL || return cached
-    pdf = PdfDim[pdfdim(d) for d in dists]
+    coefs = [logpoly(d) for d in dists]
+    pdf = PdfDim[pdfdim(d, c) for (d, c) in zip(dists, coefs)]
     src = m.rhs * "\n" * m.diffusion * "\n" * m.hmap * "\n" * m.observable
     # saveat of the ODEProblem (docs/src/tutorials/introduction.md:207-212): the observable is then an
     # `observable_at(k, t, u, p, out)` source and nout = length(saveat) * outputs per save time
     saves = collect(Float64, get(prob.kwargs, :saveat, Float64[]))
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve u0 p pdf src ens saves dists begin
+    GC.@preserve u0 p pdf src ens saves dists coefs begin
         cm = CModel(sizeof(CModel), length(u0), length(p), length(pdf), m.nout, solver, n_kkl, ens.fp32 ? 1 : 0,
                     Base.unsafe_convert(Cstring, src), pointer(u0), pointer(p),
                     prob.tspan[1], prob.tspan[2], get(kw, :abstol, default_tol[1]), get(kw, :reltol, default_tol[2]),
@@ -209,7 +233,7 @@ function SciMLBase.solve(exprob::B200Problem, expalg::MonteCarlo; block = 1 << 2
     total = zeros(nout); s = zeros(nout); s2 = zeros(nout); c = Ref(Counters(0, 0, 0, 0))
     done = 0; n = expalg.trajectories
     ens = exprob.S.ensemblealg
-    if ens.sampler === :device
+    if ens.sampler === :device && all(device_samplable, density_factors(ens, exprob.d))
         # rand(d) hoisted into the kernel: samples 0 .. n-1 of the counter-based stream `seed`; the CPU arm gets
         # the identical set from b200e_sample_host(model, seed, 0, n, 0, x)
         check(ccall((:b200e_reduce_generated, LIB), Cint,

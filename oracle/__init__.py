@@ -170,6 +170,11 @@ class OracleProblem:
         for a, d in zip(arr, dims):
             kind, lo, hi, mu, sigma = d[:5]
             a.kind, a.lo, a.hi, a.mu, a.sigma = int(kind), float(lo), float(hi), float(mu), float(sigma)
+            if int(kind) == 5:  # log-polynomial density: (5, lo, hi, 0, 1, [c0 .. c5])
+                tab = np.ascontiguousarray(d[5], dtype=np.float64)
+                assert tab.shape == (6,)
+                self._keep.append(tab)
+                a.table, a.ntable = tab.ctypes.data_as(C.POINTER(C.c_double)), 6
             if int(kind) == 4:  # tabulated density: (4, lo, hi, 0, 1, grid values) -> spline coefficients
                 vals = np.ascontiguousarray(d[5], dtype=np.float64)
                 tab = kde_prefilter(vals)

@@ -139,6 +139,14 @@ static double logpdf_1d(const orc_pdf_dim *d, double x) {
         double v = kde_pdf_1d(d, x);
         return v > 0 ? log(v) : -INFINITY;
     }
+    case ORC_PDF_LOGPOLY: { /* Distributions.logpdf of the exponential-family factors, coefficients from the caller */
+        if (!(x >= d->lo && x <= d->hi)) return -INFINITY;
+        const double *c = d->table;
+        double lp = c[0] + c[1] * x + c[2] * x * x;
+        if (c[3] != 0.0 || c[5] != 0.0) { const double lx = log(x); lp += (c[5] != 0.0 ? c[5] * lx + c[3] : c[3]) * lx; } /* nested, and no 0 * inf: defined at x = 0 */
+        if (c[4] != 0.0) lp += c[4] * log1p(-x);
+        return lp;
+    }
     case ORC_PDF_TRUNCNORMAL: {
         if (!(x >= d->lo && x <= d->hi)) return -INFINITY;
         double z = (x - d->mu) / d->sigma;

@@ -46,7 +46,8 @@ typedef void (*orc_obs_fn)(const double *u_end, const double *p, double t_end, d
  * interpolated state; writes the nout / nsave outputs of slot k */
 typedef void (*orc_obs_at_fn)(int k, double t_k, const double *u_k, const double *p, double *out_k);
 
-enum { ORC_PDF_NONE = 0, ORC_PDF_UNIFORM = 1, ORC_PDF_NORMAL = 2, ORC_PDF_TRUNCNORMAL = 3, ORC_PDF_TABLE = 4 };
+enum { ORC_PDF_NONE = 0, ORC_PDF_UNIFORM = 1, ORC_PDF_NORMAL = 2, ORC_PDF_TRUNCNORMAL = 3, ORC_PDF_TABLE = 4,
+       ORC_PDF_LOGPOLY = 5 /* logpdf = c0 + c1 x + c2 x^2 + c3 log x + c4 log(1-x) + c5 log(x)^2 on [lo, hi]; table = c0..c5 */ };
 
 /* one factor of GenericDistribution(dists...), reference distribution_utils.jl:40-48 */
 typedef struct {

@@ -23,7 +23,7 @@ OK, ERR_INVALID, ERR_COMPILE, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_NCCL = 0, 
 SOLVER_TSIT5, SOLVER_EM, SOLVER_LAMBA_EM = 0, 1, 2
 FP64, FP32 = 0, 1
 LAYOUT_POINT_MAJOR, LAYOUT_SOA = 0, 1
-PDF_NONE, PDF_UNIFORM, PDF_NORMAL, PDF_TRUNCNORMAL, PDF_TABLE = 0, 1, 2, 3, 4
+PDF_NONE, PDF_UNIFORM, PDF_NORMAL, PDF_TRUNCNORMAL, PDF_TABLE, PDF_LOGPOLY = 0, 1, 2, 3, 4, 5
 SCHED_DYNAMIC, SCHED_STATIC, SCHED_DYNAMIC_REPRODUCIBLE = 0, 1, 2
 
 _ERR_NAMES = {ERR_INVALID: "B200E_ERR_INVALID", ERR_COMPILE: "B200E_ERR_COMPILE", ERR_CUDA: "B200E_ERR_CUDA",
@@ -237,6 +237,12 @@ class ModelSpec:
             for a, d in zip(arr, self.pdf):
                 kind, lo, hi, mu, sigma = d[:5]
                 a.kind, a.lo, a.hi, a.mu, a.sigma = int(kind), float(lo), float(hi), float(mu), float(sigma)
+                if int(kind) == PDF_LOGPOLY:  # (PDF_LOGPOLY, lo, hi, 0, 1, [c0 .. c5]): log-polynomial density
+                    tab = np.ascontiguousarray(d[5], dtype=np.float64)
+                    if tab.shape != (6,):
+                        raise ValueError("a PDF_LOGPOLY factor takes exactly six coefficients c0 .. c5")
+                    keep.append(tab)
+                    a.table, a.ntable = tab.ctypes.data_as(C.POINTER(C.c_double)), 6
                 if int(kind) == PDF_TABLE:  # (PDF_TABLE, lo, hi, 0, 1, values): tabulated density on a uniform grid
                     tab = np.ascontiguousarray(d[5], dtype=np.float64)
                     keep.append(tab)

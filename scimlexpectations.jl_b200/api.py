@@ -30,7 +30,7 @@ import numpy as np
 from scipy.special import ndtr, ndtri
 
 from . import _capi
-from ._capi import (FP32, FP64, LAYOUT_POINT_MAJOR, ModelSpec, PDF_NORMAL, PDF_TABLE, PDF_TRUNCNORMAL,
+from ._capi import (FP32, FP64, LAYOUT_POINT_MAJOR, ModelSpec, PDF_LOGPOLY, PDF_NORMAL, PDF_TABLE, PDF_TRUNCNORMAL,
                     PDF_UNIFORM)
 from .cubature import hcubature_v
 
@@ -93,6 +93,104 @@ class Truncated:
 
     def table(self):
         return (PDF_TRUNCNORMAL, self.lower, self.upper, self.untruncated.mu, self.untruncated.sigma)
+
+
+class _LogPoly:
+    """A factor whose log-density is ``c0 + c1 x + c2 x^2 + c3 log x + c4 log(1 - x) + c5 log(x)^2`` on its support
+    (``B200E_PDF_LOGPOLY``): the exponential-family members of Distributions.jl a prior is usually built from.  The
+    device has no inverse CDF for them: ``MonteCarlo`` ships host samples (``scipy.stats`` quantiles of the block-keyed
+    uniform stream) for a density that holds one."""
+    device_sampler = False
+    _frozen = None   # scipy.stats frozen distribution
+
+    def coefficients(self):   # (c0, c1, c2, c3, c4, c5) on the untruncated support
+        raise NotImplementedError
+
+    def minimum(self): return float(self._frozen.support()[0])
+    def maximum(self): return float(self._frozen.support()[1])
+
+    def logpdf(self, x):
+        if not (self.minimum() <= x <= self.maximum()):
+            return -math.inf
+        c = self.coefficients()
+        lp = c[0] + c[1] * x + c[2] * x * x
+        if c[3] or c[5]:
+            lx = math.log(x) if x > 0 else -math.inf
+            lp += (c[5] * lx + c[3]) * lx if c[5] else c[3] * lx
+        if c[4]:
+            lp += c[4] * math.log1p(-x) if x < 1 else -math.inf
+        return lp
+
+    def cdf(self, x): return float(self._frozen.cdf(x))
+    def icdf(self, u): return self._frozen.ppf(u)
+    def table(self): return (PDF_LOGPOLY, self.minimum(), self.maximum(), 0.0, 1.0, np.asarray(self.coefficients(), dtype=np.float64))
+
+
+class Exponential(_LogPoly):
+    """``Exponential(theta)`` (scale): logpdf = -log(theta) - x / theta on [0, inf)."""
+    def __init__(self, theta: float = 1.0):
+        from scipy import stats
+        self.theta = float(theta)
+        self._frozen = stats.expon(scale=self.theta)
+
+    def coefficients(self): return (-math.log(self.theta), -1.0 / self.theta, 0.0, 0.0, 0.0, 0.0)
+
+
+class Gamma(_LogPoly):
+    """``Gamma(alpha, theta)`` (shape, scale): logpdf = (alpha - 1) log x - x / theta - lgamma(alpha) - alpha log(theta)."""
+    def __init__(self, alpha: float = 1.0, theta: float = 1.0):
+        from scipy import stats
+        self.alpha, self.theta = float(alpha), float(theta)
+        self._frozen = stats.gamma(self.alpha, scale=self.theta)
+
+    def coefficients(self):
+        return (-math.lgamma(self.alpha) - self.alpha * math.log(self.theta), -1.0 / self.theta, 0.0, self.alpha - 1.0, 0.0, 0.0)
+
+
+class Beta(_LogPoly):
+    """``Beta(alpha, beta)``: logpdf = (alpha - 1) log x + (beta - 1) log(1 - x) - lbeta(alpha, beta) on [0, 1]."""
+    def __init__(self, alpha: float = 1.0, beta: float = 1.0):
+        from scipy import stats
+        self.alpha, self.beta = float(alpha), float(beta)
+        self._frozen = stats.beta(self.alpha, self.beta)
+
+    def coefficients(self):
+        lbeta = math.lgamma(self.alpha) + math.lgamma(self.beta) - math.lgamma(self.alpha + self.beta)
+        return (-lbeta, 0.0, 0.0, self.alpha - 1.0, self.beta - 1.0, 0.0)
+
+
+class LogNormal(_LogPoly):
+    """``LogNormal(mu, sigma)``: logpdf = -log x - log(sigma) - log(2 pi)/2 - (log x - mu)^2 / (2 sigma^2) on (0, inf)."""
+    def __init__(self, mu: float = 0.0, sigma: float = 1.0):
+        from scipy import stats
+        self.mu, self.sigma = float(mu), float(sigma)
+        self._frozen = stats.lognorm(self.sigma, scale=math.exp(self.mu))
+
+    def coefficients(self):
+        s2 = self.sigma * self.sigma
+        return (-math.log(self.sigma) - 0.5 * math.log(2.0 * math.pi) - self.mu * self.mu / (2.0 * s2), 0.0, 0.0,
+                self.mu / s2 - 1.0, 0.0, -1.0 / (2.0 * s2))
+
+
+class TruncatedLogPoly(_LogPoly):
+    """``truncated(d, lower, upper)`` of one of the above: the same coefficients with ``-log(cdf(upper) - cdf(lower))``
+    folded into ``c0`` (Distributions.logpdf of a Truncated), support ``[lower, upper]``."""
+    def __init__(self, d: _LogPoly, lower: float, upper: float):
+        self.untruncated, self.lower, self.upper = d, max(float(lower), d.minimum()), min(float(upper), d.maximum())
+        if not self.upper > self.lower:
+            raise ValueError("empty truncation interval")
+        self._a, self._b = d.cdf(self.lower), d.cdf(self.upper)
+
+    def minimum(self): return self.lower
+    def maximum(self): return self.upper
+
+    def coefficients(self):
+        c = list(self.untruncated.coefficients())
+        c[0] -= math.log(self._b - self._a)
+        return tuple(c)
+
+    def cdf(self, x): return (self.untruncated.cdf(min(max(x, self.lower), self.upper)) - self._a) / (self._b - self._a)
+    def icdf(self, u): return np.clip(self.untruncated.icdf(self._a + (self._b - self._a) * np.asarray(u)), self.lower, self.upper)
 
 
 class UnivariateKDE:
@@ -169,10 +267,14 @@ class UnivariateKDE:
         return (PDF_TABLE, float(self.x[0]), float(self.x[-1]), 0.0, 1.0, self.density)
 
 
-def truncated(d: Normal, lower: float, upper: float) -> Truncated:
-    if not isinstance(d, Normal):
-        raise TypeError("only truncated Normal distributions are tabulated for the device pdf")
-    return Truncated(d, float(lower), float(upper))
+def truncated(d, lower: float, upper: float):
+    """``truncated(d, lower, upper)``: Normal (its own device kind, which the in-kernel sampler can draw) and the
+    log-polynomial factors (Exponential, Gamma, Beta, LogNormal)."""
+    if isinstance(d, Normal):
+        return Truncated(d, float(lower), float(upper))
+    if isinstance(d, _LogPoly):
+        return TruncatedLogPoly(d, lower, upper)
+    raise TypeError("truncated() takes a Normal or one of Exponential / Gamma / Beta / LogNormal")
 
 
 class GenericDistribution:
@@ -568,11 +670,11 @@ def _solve_montecarlo(prob: ExpectationProblem, alg: MonteCarlo):
         s, _, c = h.reduce_samples(alg.samples, weight_by_pdf=False, npts=n)
         total += s
         counters = c
-    elif alg.sampler == "device":
+    elif alg.sampler == "device" and all(getattr(f, "device_sampler", True) for f in prob.d.dists):
         s, _, c = h.reduce_generated(alg.seed, n)
         total += s
         counters = c
-    elif alg.sampler != "host":
+    elif alg.sampler not in ("host", "device"):
         raise ValueError(f"unknown sampler {alg.sampler!r} (device | host)")
     else:
         done, b = 0, 0

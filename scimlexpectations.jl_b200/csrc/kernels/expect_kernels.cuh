@@ -23,6 +23,10 @@
 
 #define B200E_FULL 0xffffffffu
 
+#ifndef B200E_LOGPOLY_PDF
+#define B200E_LOGPOLY_PDF 0
+#endif
+
 namespace b200e {
 
 constexpr int N = B200E_NSTATE;
@@ -59,6 +63,17 @@ __device__ __forceinline__ double pdf_weight(const b200e_kparams &P, const doubl
                     v = fma(0.5 * dm * dm, cm, fma(0.75 - d * d, c0, 0.5 * dp * dp * cp));
                 }
                 tabulated *= v;
+            } else if (B200E_LOGPOLY_PDF && kind == 5) {  // compiled in only when the model has such a factor
+                // logpdf = c0 + c1 x + c2 x^2 + c3 log x + c4 log(1 - x) + c5 log(x)^2  (Exponential, Gamma, Beta,
+                // LogNormal, Rayleigh, ... and their truncations; the coefficients sit in the sampler's fields)
+                const double c3 = P.pdf[j].smp_a, c4 = P.pdf[j].smp_b, c5 = P.pdf[j].smp_c;
+                double lp = fma(fma(P.pdf[j].inv_sigma, xj, P.pdf[j].mu), xj, P.pdf[j].logc);
+                if (c3 != 0.0 || c5 != 0.0) {
+                    const double lx = log(xj);
+                    lp = fma(c5 != 0.0 ? fma(c5, lx, c3) : c3, lx, lp);   // no 0 * inf at x = 0
+                }
+                if (c4 != 0.0) lp = fma(c4, log1p(-xj), lp);
+                s += inside ? lp : neg_inf();
             } else {
                 const double z = (xj - P.pdf[j].mu) * P.pdf[j].inv_sigma;
                 const double lp = fma(-0.5 * z, z, P.pdf[j].logc);

@@ -97,6 +97,10 @@ int main(int argc, char **argv) {
             k.logc = -std::log(sg) - 0.91893853320467274178 - std::log(tp);
             k.smp_a = mu; k.smp_b = sg; k.smp_c = std_normal_cdf((lo - mu) / sg); k.smp_d = tp;
         }
+        if (k.kind == 5) {  // log-polynomial: the six coefficients follow the five common fields
+            k.lo = lo; k.hi = hi; k.logc = pdf[j][5]; k.mu = pdf[j][6]; k.inv_sigma = pdf[j][7];
+            k.smp_a = pdf[j][8]; k.smp_b = pdf[j][9]; k.smp_c = pdf[j][10];
+        }
     }
     std::vector<double> kkl;
 #if B200E_SOLVER == 1

@@ -35,6 +35,7 @@ def _build(sme, spec, tmp, *, repro=0, em_spt=2, fp32=0):
     defs = dict(B200E_NSTATE=spec.nstate, B200E_NPARAM=spec.nparam, B200E_NX=spec.nx, B200E_NOUT=spec.nout,
                 B200E_NKKL=max(1, spec.n_kkl), B200E_SOLVER=spec.solver, B200E_FP32=fp32, B200E_BLOCK=BLOCK, B200E_MINBLOCKS=1,
                 B200E_DYNAMIC=1, B200E_REPRO=repro, B200E_NSAVE=len(spec.save_times), B200E_TABLE_PDF=0,
+                B200E_LOGPOLY_PDF=int(any(int(d[0]) == 5 for d in spec.pdf)),
                 B200E_CLIP_DTMAX=clip, B200E_EM_SPT=em_spt)
     cmd = [gxx, "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-I", EMUL, "-I", CSRC, "-I", os.path.join(CSRC, "kernels")]
     cmd += [f"-D{k}={v}" for k, v in defs.items()] + [f'-DMODEL_FILE="{model}"', os.path.join(EMUL, "driver.cpp"), "-o", exe]
@@ -51,7 +52,7 @@ def _run(exe, spec, tmp, x, mode, *, grid=3, weight=1, layout=0, refill=0, gen=(
              f"tol {spec.abstol!r} {spec.reltol!r}", f"dtmax {spec.dtmax!r}", f"dt_fixed {spec.dt_fixed!r}",
              f"maxiters {spec.maxiters}", f"refill {refill}", "u0 " + " ".join(repr(float(v)) for v in spec.u0),
              "p " + " ".join(repr(float(v)) for v in spec.p), f"gen {gen[0]} {gen[1]}"]
-    lines += ["pdf " + " ".join(repr(float(v)) for v in d[:5]) for d in spec.pdf]
+    lines += ["pdf " + " ".join(repr(float(v)) for v in (list(d[:5]) + (list(d[5]) if int(d[0]) == 5 else []))) for d in spec.pdf]
     lines += ["save " + " ".join(repr(float(t)) for t in spec.save_times)] if len(spec.save_times) else []
     lines += [f"mode {mode}", f"xfile {xfile}", f"outfile {out}"]
     cfg = os.path.join(tmp, "cfg.txt")
@@ -239,6 +240,29 @@ def test_wide_observable_register_accumulators_on_the_cpu(sme, tmp_path):
     for mode in ("reduce", "reduce_dyn"):
         _, _, s, s2, c, _ = _run(exe, spec, tmp, x, mode, weight=0, grid=2)
         assert c == co and np.allclose(s, so, rtol=1e-9, atol=1e-12) and np.allclose(s2, s2o, rtol=1e-9)
+
+
+def test_logpoly_density_factors_on_the_cpu(sme, tmp_path):
+    """B200E_PDF_LOGPOLY in the kernel source: Gamma / LogNormal / Exponential / Beta-shaped factors, including
+    points on and outside the support's ends."""
+    pdf = [sme.truncated(sme.Gamma(9.0, 1.5 / 9.0), 1.0, 2.0).table(), sme.truncated(sme.LogNormal(0.0, 0.4), 0.5, 1.5).table(),
+           sme.truncated(sme.Exponential(3.0), 2.0, 4.0).table(),
+           (sme._capi.PDF_LOGPOLY, 0.0, 1.5, 0.0, 1.0, np.array([0.3, 0.0, 0.0, 1.5, 0.0, 0.0]))]   # x^1.5 on [0, 1.5]
+    spec = sme.models.builtin("lotka_volterra").replace(pdf=pdf)
+    exe = _build(sme, spec, str(tmp_path))
+    x = sample_points("lotka_volterra", 300, seed=17)
+    x[0, 3] = 0.0        # log(0) * c3 > 0: weight 0, not NaN
+    x[1, 0] = 2.5        # outside
+    x[2, 2] = 4.0        # on the upper end
+    orc = oracle.OracleProblem.builtin("lotka_volterra")
+    orc.set_pdf(pdf)
+    ref, cref, sref = orc.eval_nodes(x, weight_by_pdf=True, want_steps=True)
+    dx, steps, _, _, c, _ = _run(exe, spec, str(tmp_path), x, "nodes_dyn")
+    _check_nodes(dx, steps, c, ref, cref, sref, tol=2e-6)
+    assert np.all(dx[0] == 0.0) and np.all(dx[1] == 0.0) and np.all(dx[2] != 0.0)
+    _, _, s, s2, c, _ = _run(exe, spec, str(tmp_path), x, "reduce_dyn")
+    so, s2o, co = orc.reduce_samples(x, weight_by_pdf=True)
+    _check_sums(s, s2, c, so, s2o, co)
 
 
 def test_controller_limits_and_failures_on_the_cpu(sme, tmp_path):
