@@ -283,7 +283,20 @@ __device__ __forceinline__ void block_reduce_store(const b200e_kparams &P, Accum
 // ------------------------------------------------------------------------------------------
 __shared__ b200e_tabs sh_tab;
 
-enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2 };
+// Where a lane is: EMPTY (no trajectory), ACTIVE (stepping), DONE (reached t1), FAILED (aborted in a loop header: a
+// finished trajectory in its own state rather than DONE plus a flag -- the flag was one more value live across the step
+// loop and cost a save / restore pair of moves per attempt).  (Tried: the state in the top bits of the accepted-step
+// counter, no separate variable at all -- ptxas spends the saved instructions on moves around the counter.)
+enum { LANE_EMPTY = 0, LANE_ACTIVE = 1, LANE_DONE = 2, LANE_FAILED = 3 };
+template <class LaneT> __device__ __forceinline__ bool lane_active(const LaneT &L) { return L.state == LANE_ACTIVE; }
+template <class LaneT> __device__ __forceinline__ bool lane_empty(const LaneT &L) { return L.state == LANE_EMPTY; }
+template <class LaneT> __device__ __forceinline__ bool lane_finished(const LaneT &L) { return L.state >= LANE_DONE; }
+template <class LaneT> __device__ __forceinline__ unsigned lane_failed(const LaneT &L) { return L.state == LANE_FAILED ? 1u : 0u; }
+template <class LaneT> __device__ __forceinline__ unsigned lane_naccept(const LaneT &L) { return L.nacc; }
+template <class LaneT> __device__ __forceinline__ void lane_set_empty(LaneT &L) { L.nacc = 0; L.state = LANE_EMPTY; }
+template <class LaneT> __device__ __forceinline__ void lane_abort(LaneT &L) { L.state = LANE_FAILED; }
+template <class LaneT> __device__ __forceinline__ void lane_start(LaneT &L, const bool active) { L.nacc = 0; L.state = active ? LANE_ACTIVE : LANE_DONE; }
+template <class LaneT> __device__ __forceinline__ void lane_accept(LaneT &L, const bool done) { L.nacc++; if (done) L.state = LANE_DONE; }
 
 #if B200E_SOLVER == 0
 constexpr unsigned NF_PER_ATTEMPT = 6u;  // RHS evaluations per attempted step
@@ -358,7 +371,7 @@ __device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long lo
     // again, so it is counted again)
 #pragma unroll
     for (int j = 0; j < N; j++) k1[j] = f0[j];
-    le2old = K_(le2_qoldinit);
+    le2old = K_(le2_qoldinit_n);
 }
 
 // One attempted Tsit5 step of the lane's trajectory (perform_step! + stepsize_controller! +
@@ -367,7 +380,6 @@ struct Lane {
     real u[N], k1[N], p[B200E_DIM(NP)];
     real t, dt, le2old;
     int state;
-    int failed;  // 0 ok, 1 aborted
     unsigned nf0, nacc, nrej;  // nf = nf0 (initial-step evaluations) + 6 * (nacc + nrej)
     int ksave;                 // time-sampled observables: next save slot
 };
@@ -391,8 +403,7 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     const real dt = pmin(L.dt, t1 - t);  // clip to the end point
     const real tnext = t + dt;
     if ((int)(L.nacc + L.nrej) >= maxiters || same_value(tnext, t)) {  // (a NaN estimate left dt = 0: tnext == t)
-        L.failed = 1;
-        L.state = LANE_DONE;
+        lane_abort(L);
         return;
     }
     // ---- perform_step!: 6 new stages, FSAL.  The stages are kept pre-multiplied by dt (kd_j = dt k_j):
@@ -447,8 +458,9 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
         ss = fma(r, r, ss);
     }
     // 1/N is a DFMA immediate when N is a power of two
-    const real e2 = ss * (((N & (N - 1)) == 0) ? R_(lit::inv_n) : K_(inv_n));  // EEst^2
-    const bool accept = le_nonneg(e2, one_plus_eps);  // sqrt(e2) <= 1  <=>  e2 <= nextafter(1); false for a NaN
+    // EEst^2 -- times N, undivided, when N is a power of two (lit::e2_scaled in expect_math.cuh)
+    const real e2 = lit::e2_scaled ? ss : ss * K_(inv_n);
+    const bool accept = le_nonneg(e2, one_plus_eps * R_(lit::e2_scale));  // sqrt(e2) <= 1  <=>  e2 <= nextafter(1); false for a NaN
 #if B200E_NSAVE > 0
     // before the controller, while the stages are still live anyway (keeps them out of its register budget)
     if (accept) {
@@ -491,15 +503,15 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
     // which the clamps on 1/q decide alone exactly as the reference's (EEst == 0 -> q = 1/qmax;
     // EEst = Inf -> dt/5), and |b2*le2old - b1*le2| <= 51 stays far inside exp_small's range.
     const real le2 = log_pos(sh_tab, e2);
-    const real hist = accept ? L.le2old : R_(0.0);
-    real qinv = exp_small(sh_tab, fma(K_(hb2), hist, fma(-K_(hb1), le2, K_(ln_gamma))));  // gamma * e2old^hb2 / e2^hb1
+    const real hist = accept ? L.le2old : R_(lit::ln_n);
+    real qinv = exp_small(sh_tab, fma(K_(hb2), hist, fma(-K_(hb1), le2, K_(ln_gamma_n))));  // gamma * e2old^hb2 / e2^hb1
     qinv = pmin(R_(lit::qmax), pmax(K_(qmin), qinv));
     L.dt = dt * qinv;
 #if B200E_CLIP_DTMAX  // compiled in only when the model sets dtmax < t1 - t0
     L.dt = pmin(dtmax, L.dt);
 #endif
     if (accept) {
-        L.le2old = max_with_negative(le2, R_(lit::le2_qoldinit));  // qold = max(EEst, 1e-4); le2 is never NaN
+        L.le2old = max_with_negative(le2, R_(lit::le2_qoldinit_n));  // qold = max(EEst, 1e-4); le2 is never NaN
         // fixed_t_for_floatingpoint_error! (|t_new - t1| < 100 ulp snaps to t1) and the loop condition !(t < t1) in
         // one test: t1 - t_new < snap_tol, negative values included (the time of a finished trajectory is not used)
         const real left = t1 - tnext;
@@ -507,8 +519,7 @@ __device__ __forceinline__ void tsit5_step(Lane &L, const real t1, const real dt
         L.t = done ? t1 : tnext;
 #pragma unroll
         for (int i = 0; i < N; i++) { u[i] = un[i]; k1[i] = k7[i]; }
-        L.nacc++;
-        if (done) L.state = LANE_DONE;
+        lane_accept(L, done);
     } else {
         // NaN estimate: the reference counts a rejection, dt turns NaN and the solve aborts at the next
         // loop header -- same here through dt = 0 (t + dt == t aborts there; tested on this rarely taken side only)
@@ -538,7 +549,6 @@ struct Lane {
     real u[N], zc[NK], p[B200E_DIM(NP)];  // zc_k = Z_k sqrt(2) / ((k-1/2) pi)
     real t, dt, le2old, wcur;
     int state;
-    int failed;
     unsigned nf0, nacc, nrej;
     int ksave;
 };
@@ -619,7 +629,7 @@ __device__ __forceinline__ void start_trajectory(const b200e_kparams &P, long lo
     L.t = t;
     L.dt = fmin(fmin(R_(100.0) * dt0, dt1), dtmax);
     L.wcur = kkl_w(L.zc, t);
-    L.le2old = K_(le2_qoldinit);
+    L.le2old = K_(le2_qoldinit_n);
     L.nf0 += 2u;
 }
 
@@ -632,8 +642,7 @@ __device__ __forceinline__ void lamba_step(Lane &L, const real t1, const real dt
     const real dt = pmin(L.dt, t1 - t);  // modify_dt_for_tstops!
     const real tnext = t + dt;
     if ((int)(L.nacc + L.nrej) >= maxiters || same_value(tnext, t)) {  // (a NaN estimate left dt = 0: tnext == t)
-        L.failed = 1;
-        L.state = LANE_DONE;
+        lane_abort(L);
         return;
     }
     real f0[N], K[N], Lg[N], un[N], f1[N], v[N], g1[N];
@@ -660,27 +669,26 @@ __device__ __forceinline__ void lamba_step(Lane &L, const real t1, const real dt
         const real r = num * rcp_pos(sc);
         ss = fma(r, r, ss);
     }
-    const real e2 = ss * R_(lit::inv_n);                // EEst^2
-    const bool accept = le_nonneg(e2, one_plus_eps);    // false for a NaN
+    const real e2 = lit::e2_scaled ? ss : ss * R_(lit::inv_n);                 // EEst^2 (times N: see tsit5_step)
+    const bool accept = le_nonneg(e2, one_plus_eps * R_(lit::e2_scale));      // false for a NaN
     // PI controller in log space on e2 (see tsit5_step): EEst^b1 = e2^(b1/2)
     const real le2 = log_pos(sh_tab, e2);
-    const real hist = accept ? L.le2old : R_(0.0);
-    real qinv = exp_small(sh_tab, fma(K_(sde_hb2), hist, fma(-K_(sde_hb1), le2, K_(ln_gamma))));  // gamma qold^b2 / EEst^b1
+    const real hist = accept ? L.le2old : R_(lit::ln_n);
+    real qinv = exp_small(sh_tab, fma(K_(sde_hb2), hist, fma(-K_(sde_hb1), le2, K_(sde_ln_gamma_n))));  // gamma qold^b2 / EEst^b1
     qinv = pmin(R_(1.125), pmax(K_(qmin), qinv));
     L.dt = dt * qinv;
 #if B200E_CLIP_DTMAX
     L.dt = pmin(dtmax, L.dt);
 #endif
     if (accept) {
-        L.le2old = max_with_negative(le2, R_(lit::le2_qoldinit));
+        L.le2old = max_with_negative(le2, R_(lit::le2_qoldinit_n));
         const real left = t1 - tnext;
         const bool done = lt_any_pos(left, snap_tol);  // fixed_t_for_floatingpoint_error! and !(t < t1), see tsit5_step
         L.t = done ? t1 : tnext;
 #pragma unroll
         for (int i = 0; i < N; i++) u[i] = un[i];
         L.wcur = wn;
-        L.nacc++;
-        if (done) L.state = LANE_DONE;
+        lane_accept(L, done);
     } else {
         if (!(e2 == e2)) L.dt = R_(0.0);   // NaN estimate: abort at the next loop header
         L.nrej++;
@@ -706,8 +714,8 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
 #if B200E_SOLVER == 2
     L.wcur = R_(0.0);
 #endif
-    L.state = LANE_EMPTY; L.failed = 0;
-    L.nf0 = 0; L.nacc = 0; L.nrej = 0; L.ksave = 0;
+    L.nf0 = 0; L.nrej = 0; L.ksave = 0;
+    lane_set_empty(L);
     double wgt = 1.0;
     Accum A;
     A.init();
@@ -756,17 +764,17 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
     }
     for (;;) {
         // ---- refill phase: runs only when the set of stepping lanes has changed ----
-        const bool wants = (L.state == LANE_DONE) ||
-                           (L.state == LANE_EMPTY && (dyn ? (more || (repro && sc_left > 0)) : next < P.npts));
+        const bool wants = lane_finished(L) ||
+                           (lane_empty(L) && (dyn ? (more || (repro && sc_left > 0)) : next < P.npts));
         const unsigned idle_m = __ballot_sync(B200E_FULL, wants);
-        unsigned act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
+        unsigned act_m = __ballot_sync(B200E_FULL, lane_active(L));
         if ((idle_m | act_m) == 0u) break;
         const int live = __popc(idle_m | act_m);
         const int thr = thr_eff < live ? thr_eff : live;
         if (__popc(idle_m) >= thr) {  // warp-uniform
-            const unsigned done_m = __ballot_sync(B200E_FULL, L.state == LANE_DONE);
+            const unsigned done_m = __ballot_sync(B200E_FULL, lane_finished(L));
             if (tune && done_m == B200E_FULL) {  // first full generation finished: measure its imbalance
-                const unsigned st = L.nacc + L.nrej;
+                const unsigned st = lane_naccept(L) + L.nrej;
                 const unsigned mx = __reduce_max_sync(B200E_FULL, st), sm = __reduce_add_sync(B200E_FULL, st);
                 if (mx * 128u > sm * 5u) thr_eff = 8;  // max > 1.25 * mean
                 tune = false;
@@ -777,7 +785,7 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 // trajectory of this chunk, and their squares, into the lane's accumulator columns (unused otherwise
                 // under this schedule); aborted trajectories add their NaN slots now.  Chunk sums in a fixed order,
                 // then the columns are cleared for the next chunk.
-                if (L.state == LANE_DONE) emit_missing<REDUCE>(P, cur, L.ksave, wgt, A);
+                if (lane_finished(L)) emit_missing<REDUCE>(P, cur, L.ksave, wgt, A);
 #pragma unroll 1
                 for (int k = 0; k < NACC; k++) {
                     double v = A.val(k);
@@ -793,10 +801,10 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 real out[NOUT];
 #pragma unroll
                 for (int k = 0; k < NOUT; k++) out[k] = R_(0.0);
-                if (L.state == LANE_DONE) observable(L.u, L.p, (real)P.t1, out);
+                if (lane_finished(L)) observable(L.u, L.p, (real)P.t1, out);
 #pragma unroll 1
                 for (int k = 0; k < NOUT; k++) {
-                    double v = (L.state == LANE_DONE) ? (double)out[k] : 0.0;
+                    double v = lane_finished(L) ? (double)out[k] : 0.0;
                     if (P.weight_by_pdf) v *= wgt;
                     double v2 = v * v;
 #pragma unroll
@@ -811,15 +819,16 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
                 }
             }
 #endif
-            if (L.state == LANE_DONE) {
+            if (lane_finished(L)) {
 #if B200E_NSAVE > 0
                 if (!repro) emit_missing<REDUCE>(P, cur, L.ksave, wgt, A);
 #else
                 if (!repro) emit<REDUCE>(P, cur, L.u, L.p, wgt, A);
 #endif
-                if (!REDUCE && P.steps) P.steps[cur] = (int)(L.nacc + L.nrej);
-                A.count(L.nf0 + NF_PER_ATTEMPT * (L.nacc + L.nrej), L.nacc, L.nrej, L.failed ? 1u : 0u);
-                L.state = LANE_EMPTY;
+                const unsigned nacc = lane_naccept(L);
+                if (!REDUCE && P.steps) P.steps[cur] = (int)(nacc + L.nrej);
+                A.count(L.nf0 + NF_PER_ATTEMPT * (nacc + L.nrej), nacc, L.nrej, lane_failed(L));
+                lane_set_empty(L);
             }
             if (repro) {
                 if (sc_left == 0 && sc_row >= 0) {  // the super-chunk is complete: its row leaves the warp
@@ -863,32 +872,32 @@ __device__ __forceinline__ void tsit5_run(const b200e_kparams &P) {
             if (wants && next < P.npts) {
                 cur = next;
                 next = dyn ? P.npts : next + T;
-                L.nf0 = 0; L.nacc = 0; L.nrej = 0; L.failed = 0;
+                L.nf0 = 0; L.nrej = 0;
 #if B200E_SOLVER == 2
                 start_trajectory<GEN>(P, cur, L, wgt);
 #else
                 start_trajectory<GEN>(P, cur, L.u, L.p, L.k1, L.t, L.dt, L.le2old, wgt, L.nf0);
 #endif
-                L.state = (L.t < t1) ? LANE_ACTIVE : LANE_DONE;
+                lane_start(L, L.t < t1);
 #if B200E_NSAVE > 0
                 // save times at t0 hold the initial state (save_start)
                 for (L.ksave = 0; L.ksave < NSAVE && (real)P.save_t[L.ksave] <= L.t; L.ksave++)
                     emit_slot<REDUCE>(P, cur, L.ksave, (real)P.save_t[L.ksave], L.u, L.p, wgt, A);
 #endif
             }
-            act_m = __ballot_sync(B200E_FULL, L.state == LANE_ACTIVE);
+            act_m = __ballot_sync(B200E_FULL, lane_active(L));
         }
         if (act_m == 0u) continue;
         // ---- step phase: a tight loop, one vote per step, until some lane finishes (a lane only ever goes from
         // ACTIVE to DONE in here, so "nobody finished" is one all-vote on a per-lane predicate) ----
-        const bool stepping = L.state == LANE_ACTIVE;
+        const bool stepping = lane_active(L);
         do {
 #if B200E_SOLVER == 2
-            if (L.state == LANE_ACTIVE) lamba_step<REDUCE>(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps);
+            if (lane_active(L)) lamba_step<REDUCE>(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps);
 #else
-            if (L.state == LANE_ACTIVE) tsit5_step<REDUCE>(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps, SaveCtx{P, cur, wgt, A});
+            if (lane_active(L)) tsit5_step<REDUCE>(L, t1, dtmax, abstol, reltol, snap_tol, maxiters, one_plus_eps, SaveCtx{P, cur, wgt, A});
 #endif
-        } while (__all_sync(B200E_FULL, !stepping || L.state == LANE_ACTIVE));
+        } while (__all_sync(B200E_FULL, !stepping || lane_active(L)));
     }
     block_reduce_store<REDUCE>(P, A);
 }

@@ -69,12 +69,22 @@ constexpr double log2e_128 = 128.0 * 1.4426950408889634074, ln2_128 = 0.69314718
 constexpr double rnd_magic = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-nearest-integer
 constexpr double two52_1023 = 4503599627370496.0 + 1023.0;
 constexpr double ln10_04 = 0.4 * 2.302585092994045684;
+// The controller never divides the sum of squared scaled residuals by N when N is a power of two: its "e2" is then
+// N EEst^2 -- an exact scaling -- and the shift ln N sits in the constants instead: the accept threshold is N (1 + eps),
+// the history of a rejected step reads ln N instead of 0, qoldinit and ln(gamma) carry their share.
+constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n >> 1); }
+constexpr bool e2_scaled = (B200E_NSTATE & (B200E_NSTATE - 1)) == 0;
+constexpr double e2_scale = e2_scaled ? (double)B200E_NSTATE : 1.0;
+constexpr double ln_n = e2_scaled ? ln2 * ilog2c(B200E_NSTATE) : 0.0;
+constexpr double le2_qoldinit_n = le2_qoldinit + ln_n;
+constexpr double ln_gamma_n = ln_gamma + (hb1 - hb2) * ln_n;
 // series coefficients rounded to the 21 bits a DFMA immediate carries.  Their terms are at most
 // 2^-24 (log: r^3/3, |r| <= 2^-8) resp. 2^-27 (exp: r^3/6, |r| <= 2^-8.5) of the result, so the
 // 2^-21 rounding stays below 2^-45 * 2^-8 ... i.e. under 1e-14 absolute; they cost no register.
 // LambaEM (expect_kernels.cuh): SDE PI-controller exponents on e2 (beta1/2, beta2/2) and the Taylor coefficients of
 // sin(pi r / 2) = r (sp0 + r^2 (sp1 + ... + r^2 sp10)), |r| <= 1 (next term 1.3e-18)
 constexpr double sde_hb1 = 0.5 * 7.0 / 10.0, sde_hb2 = 0.5 * 2.0 / 5.0;
+constexpr double sde_ln_gamma_n = ln_gamma + (sde_hb1 - sde_hb2) * ln_n;
 constexpr double sp0 = 1.5707963267948966192, sp1 = -0.64596409750624625366, sp2 = 0.079692626246167045121,
                  sp3 = -0.0046817541353186881007, sp4 = 0.00016044118478735982187, sp5 = -3.5988432352120853405e-6,
                  sp6 = 5.6921729219679268118e-8, sp7 = -6.6880351098114672325e-10, sp8 = 6.0669357311061956671e-12,
@@ -89,7 +99,7 @@ constexpr double sixth_i = 0x1.55555p-3, r24_i = 0x1.55555p-5;
 struct b200e_consts {
     double c1, c2, c3, c4, a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, a71,
         a72, a73, a74, a75, a76, bt1, bt2, bt3, bt4, bt5, bt6, bt7;
-    double hb1, hb2, ln_gamma, qmin, qmax, le2_qoldinit, inv_n;
+    double hb1, hb2, ln_gamma_n, sde_ln_gamma_n, qmin, qmax, le2_qoldinit_n, inv_n;
     double ln2, log2e_128, ln2_128, ln10_04, fifth, r24;
     double sde_hb1, sde_hb2, sp0, sp1, sp2, sp3, sp4, sp5, sp6, sp7, sp8, sp9, sp10;
 };
@@ -98,7 +108,7 @@ B200E_CONST b200e_consts KC = {
     lit::c1, lit::c2, lit::c3, lit::c4, lit::a21, lit::a31, lit::a32, lit::a41, lit::a42, lit::a43, lit::a51,
     lit::a52, lit::a53, lit::a54, lit::a61, lit::a62, lit::a63, lit::a64, lit::a65, lit::a71, lit::a72, lit::a73,
     lit::a74, lit::a75, lit::a76, lit::bt1, lit::bt2, lit::bt3, lit::bt4, lit::bt5, lit::bt6, lit::bt7,
-    lit::hb1, lit::hb2, lit::ln_gamma, lit::qmin, lit::qmax, lit::le2_qoldinit, lit::inv_n,
+    lit::hb1, lit::hb2, lit::ln_gamma_n, lit::sde_ln_gamma_n, lit::qmin, lit::qmax, lit::le2_qoldinit_n, lit::inv_n,
     lit::ln2, lit::log2e_128, lit::ln2_128, lit::ln10_04, 0.2, 1.0 / 24.0,
     lit::sde_hb1, lit::sde_hb2, lit::sp0, lit::sp1, lit::sp2, lit::sp3, lit::sp4, lit::sp5, lit::sp6, lit::sp7, lit::sp8,
     lit::sp9, lit::sp10};
@@ -197,18 +207,18 @@ B200E_MFN void sqrt_rsqrt_pos(double x, double &s, double &rs) {
     rs = h + h;         // 2 h -> 1/sqrt(x) to ~1.5e-12: it only scales the LambaEM error estimate (step-size control)
 }
 // log(x), x > 0:  x = 2^e m, m in [1,2), j = top 7 bits of m's fraction;
-//   log x = e ln2 + lc_j + log1p(r),  r = x * (c_j 2^-e) - 1  (one exact-product DFMA), |r| <= 2^-8,
+//   log x = e ln2 + lc_j + log1p(r),  r = m c_j - 1  (one exact-product DFMA), |r| <= 2^-8,
 //   log1p(r) = r - r^2/2 + r^3/3 - r^4/4  (next term 2^-40/5 = 1.8e-13 absolute: step-size control only, see rcp_pos).
-// c_j 2^-e is formed by subtracting x's exponent field from c_j's.  The high word is clamped so
-// +inf, NaN and sign-bit patterns read as ~2^1023: zero / subnormal x gives about -711 and those
-// about +708, for which the controller's clamps decide alone (EEst = 0 -> q = 1/qmax, EEst = Inf ->
-// dt/5 as in the reference); the result is always finite.
+// Every bit pattern gives a finite result: zero / subnormal x reads as 2^-1023 m (about -709), +inf and NaN as
+// 2^1024 m (about +710), sign-bit patterns higher still -- for all of which the controller's clamps decide alone
+// (EEst = 0 -> q = 1/qmax, EEst = Inf -> dt/5 as in the reference).
 B200E_MFN double log_pos(const b200e_tabs &T, double x) {
-    unsigned hi = (unsigned)__double2hiint(x);
-    hi = hi < 0x7fdfffffu ? hi : 0x7fdfffffu;
+    const unsigned hi = (unsigned)__double2hiint(x);
     const b200e_lgent ent = T.lg[(hi >> (20 - TAB_BITS)) & (TAB_N - 1)];
-    const int chi = __double2hiint(ent.c) - (int)(hi & 0x7ff00000u) + 0x3ff00000;
-    const double r = fma(__hiloint2double((int)hi, __double2loint(x)), __hiloint2double(chi, __double2loint(ent.c)), -1.0);
+    // the argument's mantissa under the exponent of 1.0: m in [1, 2) for EVERY bit pattern, so the exponent needs no clamp
+    // (round 1 scaled the table's reciprocal by 2^-e instead, which needed one: a VIMNMX and an IADD3 more per call)
+    const double m = __hiloint2double((int)((hi & 0x000fffffu) | 0x3ff00000u), __double2loint(x));
+    const double r = fma(m, ent.c, -1.0);
     const double ef = __hiloint2double(0x43300000, (int)(hi >> 20)) - lit::two52_1023;  // (double)e, exact
     // Horner: every DFMA has two register sources (accumulator, r) and one immediate -> 2-cycle issue
     double h = fma(r, -0.25, lit::third_i);

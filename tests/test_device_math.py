@@ -104,8 +104,8 @@ def test_table_log_exp_rcp_sqrt_accuracy(twin):
 
 def test_log_is_finite_and_saturates_for_special_values(twin):
     vals = [float(v) for v in twin[1:9]]
-    # 0 / subnormals -> about -711 (controller clamps to q = 1/qmax), huge / inf / NaN / negative
-    # patterns -> about +707 (clamps to the reject factor qmin): the kernel needs no special case
+    # 0 / subnormals -> about -709 (controller clamps to q = 1/qmax), huge / inf / NaN / negative
+    # patterns -> +709 and above (clamps to the reject factor qmin): the kernel needs no special case
     assert all(v < -700 for v in vals[:3])
     assert all(v > 700 for v in vals[3:])
 
