@@ -1,5 +1,5 @@
 """CPU fuzz of the emulated kernels (tests/cuda_emul) against the oracle on generated models: no GPU needed.
-usage: emul_fuzz.py ode|noise|large <first seed> <end seed>"""
+usage: emul_fuzz.py ode|noise|large|logpoly <first seed> <end seed>"""
 import os
 import sys
 import tempfile
@@ -8,12 +8,15 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import scimlexpectations_jl_b200 as sme
 from tests.test_kernel_emulation import _build, _run, _check_nodes
-from tests.fuzz_util import oracle_of, random_model, random_noise_model
+from tests.fuzz_util import oracle_of, random_model, random_noise_model, with_logpoly_factors
 fam=sys.argv[1]; a=int(sys.argv[2]); b=int(sys.argv[3])
 bad=0
 for seed in range(a,b):
     try:
         spec, draw = random_noise_model(seed) if fam=="noise" else random_model(seed, nmax=16 if fam=="large" else 5)
+        if fam=="logpoly":
+            spec, draw = with_logpoly_factors(seed, spec, draw)
+            if not any(int(d[0])==5 for d in spec.pdf): continue
         tmp=tempfile.mkdtemp()
         exe=_build(sme, spec, tmp, repro=1 if spec.schedule==2 else 0)
         orc=oracle_of(spec)

@@ -1,10 +1,10 @@
 """Differential run on a B200: random models (tests/fuzz_util.py) x random batch shapes, kernel against oracle.
-usage: fuzz_parity.py [first_seed] [count] [ode | large | noise]"""
+usage: fuzz_parity.py [first_seed] [count] [ode | large | noise | logpoly]"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import scimlexpectations_jl_b200 as sme
-from tests.fuzz_util import compare, oracle_of, random_model, random_noise_model
+from tests.fuzz_util import compare, oracle_of, random_model, random_noise_model, with_logpoly_factors
 
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 count = int(sys.argv[2]) if len(sys.argv) > 2 else 16
@@ -12,6 +12,11 @@ family = sys.argv[3] if len(sys.argv) > 3 else "ode"
 bad = 0
 for seed in range(first, first + count):
     spec, draw = random_noise_model(seed) if family == "noise" else random_model(seed, nmax=16 if family == "large" else 5)
+    if family == "logpoly":
+        spec, draw = with_logpoly_factors(seed, spec, draw)
+        if not any(int(d[0]) == 5 for d in spec.pdf):
+            print(f"# seed {seed}: no positive-support dimension, skipped", flush=True)
+            continue
     rng = np.random.default_rng([7, seed])
     orc = oracle_of(spec)
     t0 = time.time()

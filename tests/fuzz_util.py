@@ -96,6 +96,38 @@ def random_model(seed: int, nmax: int = 5):
     return spec, draw
 
 
+def with_logpoly_factors(seed: int, spec, draw):
+    """The same model with the density factors of its positive-support dimensions (those scattered into p, support
+    [0.5, 1.5]) replaced by log-polynomial ones (B200E_PDF_LOGPOLY): truncated Gamma / LogNormal / Exponential, or a
+    Beta on (0.5, 1) -- drawn from a separate stream so that random_model(seed) itself is unchanged."""
+    rng = np.random.default_rng([20261022, seed])
+    pdf, facs = list(spec.pdf), {}
+    for j, d in enumerate(spec.pdf):
+        if (d[1], d[2]) != (0.5, 1.5):
+            continue
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            f = sme.truncated(sme.Gamma(float(rng.uniform(0.6, 9.0)), float(rng.uniform(0.1, 1.0))), 0.5, 1.5)
+        elif kind == 1:
+            f = sme.truncated(sme.LogNormal(float(rng.uniform(-0.5, 0.5)), float(rng.uniform(0.2, 0.8))), 0.5, 1.5)
+        elif kind == 2:
+            f = sme.truncated(sme.Exponential(float(rng.uniform(0.3, 3.0))), 0.5, 1.5)
+        else:
+            f = sme.truncated(sme.Beta(float(rng.uniform(0.7, 4.0)), float(rng.uniform(0.7, 4.0))), 0.5, 1.0)
+        pdf[j], facs[j] = f.table(), f
+    if not facs:   # no parameter dimension: put a Gamma-shaped factor on a shifted copy of nothing -- leave the model as it is
+        return spec, draw
+
+    def draw2(npts: int, sseed: int = 0):
+        x = draw(npts, sseed)
+        u = np.random.default_rng([seed, sseed, 5]).random((npts, len(facs)))
+        for c, (j, f) in enumerate(facs.items()):
+            x[:, j] = f.icdf(u[:, c])
+        return x
+
+    return spec.replace(pdf=pdf), draw2
+
+
 def random_noise_model(seed: int):
     """A process-noise model (src/expectation.jl:209-249 / :295-325): 1-4 states, random drift and diffusion
     (zero / constant / linear / bounded-nonlinear per component), 1-13 KKL modes (odd and even counts), fixed-step
