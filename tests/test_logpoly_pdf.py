@@ -97,6 +97,14 @@ def test_host_validation_of_logpoly_factors(sme):
     assert np.array_equal(x, gd.rand_block(3, 0, 4000)) and not np.array_equal(x, gd.rand_block(3, 1, 4000))
 
 
+def test_handle_cache_key_sees_the_coefficients():
+    from scimlexpectations_jl_b200.api import _spec_key
+    rest = [sme.Uniform(0.5, 1.5).table(), sme.Uniform(2.0, 4.0).table(), sme.Uniform(0.5, 1.5).table()]
+    a = _spec([sme.truncated(sme.Gamma(2.0, 0.5), 1.0, 2.0).table()] + rest)
+    b = _spec([sme.truncated(sme.Gamma(2.0, 0.6), 1.0, 2.0).table()] + rest)
+    assert _spec_key(a) != _spec_key(b) and _spec_key(a) == _spec_key(_spec([sme.truncated(sme.Gamma(2.0, 0.5), 1.0, 2.0).table()] + rest))
+
+
 # the Lotka-Volterra parameters under positive-support priors, truncated to the box the builtin integrates over
 def _lv_priors():
     return [sme.truncated(sme.Gamma(9.0, 1.5 / 9.0), 1.0, 2.0), sme.truncated(sme.LogNormal(0.0, 0.4), 0.5, 1.5),
