@@ -1,7 +1,7 @@
 """Log-polynomial density factors (``B200E_PDF_LOGPOLY``, SURVEY.md 8 row a5 widened): the exponential-family
 members of Distributions.jl a ``GenericDistribution`` is usually built from -- Exponential, Gamma, Beta, LogNormal
 and their truncations -- as ``logpdf = c0 + c1 x + c2 x^2 + c3 log x + c4 log(1 - x) + c5 log(x)^2`` on the support.
-Distributions.jl is a dependency of the reference, not part of it (Project.toml: Distributions = "0.23, 0.24, 0.25");
+Distributions.jl is a dependency of the reference, not part of it (Project.toml:30, compat "0.25.88");
 its published log-densities are pinned here against ``scipy.stats`` as the independent implementation."""
 import math
 
