@@ -106,7 +106,7 @@ pdfdim(d::Truncated{<:Normal}) = PdfDim(3, 0, minimum(d), maximum(d), mean(d.unt
 # a KernelDensity.UnivariateKDE (gpu_bayesian.md:153-166); `k.density` must stay alive until b200e_create returns
 pdfdim(k::KernelDensity.UnivariateKDE) = PdfDim(4, 0, first(k.x), last(k.x), 0.0, 1.0, pointer(k.density), length(k.density))
 pdfdim(d) = error("B200Expectations: no device pdf table for $(typeof(d)); supported: Uniform, Normal, truncated(Normal), " *
-                  "Exponential, Gamma, Beta, LogNormal and their truncations, KernelDensity.UnivariateKDE")
+                  "Exponential, Gamma, Beta, LogNormal, Rayleigh, Chisq, Chi, Erlang, Pareto and their truncations, KernelDensity.UnivariateKDE")
 
 # Log-polynomial factors (B200E_PDF_LOGPOLY): logpdf = c0 + c1 x + c2 x^2 + c3 log x + c4 log(1 - x) + c5 log(x)^2 on the
 # support.  `logpoly_shape` gives c1 .. c5; c0 (the normaliser, and log(tp) of a truncation) is read off Distributions'
@@ -116,6 +116,11 @@ logpoly_shape(d::Exponential) = (-1 / scale(d), 0.0, 0.0, 0.0, 0.0)
 logpoly_shape(d::Gamma) = (-1 / scale(d), 0.0, shape(d) - 1, 0.0, 0.0)
 logpoly_shape(d::Beta) = (0.0, 0.0, params(d)[1] - 1, params(d)[2] - 1, 0.0)
 logpoly_shape(d::LogNormal) = (0.0, 0.0, params(d)[1] / params(d)[2]^2 - 1, 0.0, -1 / (2 * params(d)[2]^2))
+logpoly_shape(d::Rayleigh) = (0.0, -1 / (2 * scale(d)^2), 1.0, 0.0, 0.0)
+logpoly_shape(d::Chisq) = (-0.5, 0.0, dof(d) / 2 - 1, 0.0, 0.0)
+logpoly_shape(d::Chi) = (0.0, -0.5, dof(d) - 1, 0.0, 0.0)
+logpoly_shape(d::Erlang) = (-1 / scale(d), 0.0, shape(d) - 1.0, 0.0, 0.0)
+logpoly_shape(d::Pareto) = (0.0, 0.0, -(shape(d) + 1), 0.0, 0.0)
 logpoly_shape(d::Truncated) = d.untruncated isa Normal ? nothing : logpoly_shape(d.untruncated)
 function logpoly(d)
     s = logpoly_shape(d)

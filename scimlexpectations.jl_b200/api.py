@@ -172,6 +172,59 @@ class LogNormal(_LogPoly):
                 self.mu / s2 - 1.0, 0.0, -1.0 / (2.0 * s2))
 
 
+class Rayleigh(_LogPoly):
+    """``Rayleigh(sigma)``: logpdf = log x - x^2 / (2 sigma^2) - 2 log(sigma) on [0, inf)."""
+    def __init__(self, sigma: float = 1.0):
+        from scipy import stats
+        self.sigma = float(sigma)
+        self._frozen = stats.rayleigh(scale=self.sigma)
+
+    def coefficients(self): return (-2.0 * math.log(self.sigma), 0.0, -0.5 / (self.sigma * self.sigma), 1.0, 0.0, 0.0)
+
+
+class Chisq(_LogPoly):
+    """``Chisq(nu)`` = Gamma(nu / 2, 2)."""
+    def __init__(self, nu: float):
+        from scipy import stats
+        self.nu = float(nu)
+        self._frozen = stats.chi2(self.nu)
+
+    def coefficients(self):
+        h = 0.5 * self.nu
+        return (-math.lgamma(h) - h * math.log(2.0), -0.5, 0.0, h - 1.0, 0.0, 0.0)
+
+
+class Chi(_LogPoly):
+    """``Chi(nu)``: logpdf = (nu - 1) log x - x^2 / 2 - (nu / 2 - 1) log 2 - lgamma(nu / 2) on [0, inf)."""
+    def __init__(self, nu: float):
+        from scipy import stats
+        self.nu = float(nu)
+        self._frozen = stats.chi(self.nu)
+
+    def coefficients(self):
+        h = 0.5 * self.nu
+        return (-(h - 1.0) * math.log(2.0) - math.lgamma(h), 0.0, -0.5, self.nu - 1.0, 0.0, 0.0)
+
+
+class Erlang(Gamma):
+    """``Erlang(k, theta)`` = Gamma with an integer shape."""
+    def __init__(self, k: int = 1, theta: float = 1.0):
+        if int(k) != k or k < 1:
+            raise ValueError("Erlang takes a positive integer shape")
+        super().__init__(float(k), theta)
+
+
+class Pareto(_LogPoly):
+    """``Pareto(alpha, theta)`` (shape, scale): logpdf = log(alpha) + alpha log(theta) - (alpha + 1) log x on [theta, inf)."""
+    def __init__(self, alpha: float = 1.0, theta: float = 1.0):
+        from scipy import stats
+        self.alpha, self.theta = float(alpha), float(theta)
+        self._frozen = stats.pareto(self.alpha, scale=self.theta)
+
+    def coefficients(self):
+        return (math.log(self.alpha) + self.alpha * math.log(self.theta), 0.0, 0.0, -(self.alpha + 1.0), 0.0, 0.0)
+
+
 class TruncatedLogPoly(_LogPoly):
     """``truncated(d, lower, upper)`` of one of the above: the same coefficients with ``-log(cdf(upper) - cdf(lower))``
     folded into ``c0`` (Distributions.logpdf of a Truncated), support ``[lower, upper]``."""
@@ -269,12 +322,13 @@ class UnivariateKDE:
 
 def truncated(d, lower: float, upper: float):
     """``truncated(d, lower, upper)``: Normal (its own device kind, which the in-kernel sampler can draw) and the
-    log-polynomial factors (Exponential, Gamma, Beta, LogNormal)."""
+    log-polynomial factors (Exponential, Gamma, Beta, LogNormal, Rayleigh, Chisq, Chi, Erlang, Pareto)."""
     if isinstance(d, Normal):
         return Truncated(d, float(lower), float(upper))
     if isinstance(d, _LogPoly):
         return TruncatedLogPoly(d, lower, upper)
-    raise TypeError("truncated() takes a Normal or one of Exponential / Gamma / Beta / LogNormal")
+    raise TypeError("truncated() takes a Normal or a log-polynomial factor (Exponential, Gamma, Beta, LogNormal, Rayleigh, Chisq, "
+                    "Chi, Erlang, Pareto)")
 
 
 class GenericDistribution:

@@ -22,6 +22,11 @@ FAMILIES = [
     (lambda: sme.Beta(0.6, 0.8), st.beta(0.6, 0.8)),
     (lambda: sme.LogNormal(0.3, 0.45), st.lognorm(0.45, scale=math.exp(0.3))),
     (lambda: sme.LogNormal(0.2, math.sqrt(0.2)), st.lognorm(math.sqrt(0.2), scale=math.exp(0.2))),   # c3 == 0, c5 != 0
+    (lambda: sme.Rayleigh(1.3), st.rayleigh(scale=1.3)),
+    (lambda: sme.Chisq(5.0), st.chi2(5.0)),
+    (lambda: sme.Chi(3.0), st.chi(3.0)),
+    (lambda: sme.Erlang(3, 0.5), st.gamma(3.0, scale=0.5)),
+    (lambda: sme.Pareto(2.5, 0.8), st.pareto(2.5, scale=0.8)),
 ]
 
 
