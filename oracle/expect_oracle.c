@@ -8,7 +8,12 @@
  *                  algorithms -- Tsitouras 2011 5(4) pair, Hairer-Wanner initial step,
  *                  PI step-size control, Euler-Maruyama)
  *   output_func (expectation.jl:180, :227, :282, :316)
- *   pdf        (src/distribution_utils.jl:42, :50 -> Distributions.logpdf)
+ *   pdf        (src/distribution_utils.jl:42, :50 -> Distributions.logpdf: third-party, not vendored -- Uniform,
+ *               Normal and truncated Normal restated from the published densities; the exponential-family factors
+ *               (Exponential, Gamma, Beta, LogNormal, Rayleigh, Chisq, Chi, Erlang, Pareto and their truncations)
+ *               through ONE log-polynomial case whose coefficients the caller supplies, pinned against
+ *               scipy.stats in tests/test_logpoly_pdf.py; KernelDensity's pdf(kde, x) as Interpolations'
+ *               quadratic B-spline, tests/test_table_pdf.py)
  *   reduction  (expectation.jl:194 per-node, :293 mean)
  */
 #include "expect_oracle.h"
